@@ -1,0 +1,112 @@
+/*
+ * b200sa.h -- C-ABI of the B200-native suffix-array / LCP construction engine.
+ *
+ * Drop-in boundary for the construction hot path of BurntSushi/suffix
+ * (reference: /root/reference/src/table.rs).  The reference has no FFI of its
+ * own; the seam is the two private calls made by its public API:
+ *
+ *   SuffixTable::new      -> sais_table(&text)            src/table.rs:83, :378-386
+ *   SuffixTable::lcp_lens -> lcp_lens_quadratic(text,sa)  src/table.rs:135, :348-361
+ *
+ * Every entry point takes plain pointers and sizes (no torch / C++ types).
+ * Caller owns every buffer passed in; the library never retains host
+ * pointers after return.  Device workspace is owned by the context and is
+ * reused across calls.  A context is NOT thread-safe; distinct contexts are.
+ * There is NO CPU fallback: without a usable CUDA device every call returns
+ * B200SA_ERR_NO_DEVICE / B200SA_ERR_CUDA.
+ *
+ * Suffix indices are byte offsets stored as u32 (reference: src/table.rs:64-66),
+ * so n must be <= 2^32-1 (the reference asserts the same, src/table.rs:380).
+ */
+#ifndef B200SA_H
+#define B200SA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200sa_ctx b200sa_ctx;
+
+enum {
+    B200SA_OK            =  0,
+    B200SA_ERR_BAD_ARG   = -1,  /* null pointer / bad size                        */
+    B200SA_ERR_TOO_LARGE = -2,  /* n > 2^32-1: reference panics, src/table.rs:380 */
+    B200SA_ERR_NO_DEVICE = -3,
+    B200SA_ERR_OOM       = -4,
+    B200SA_ERR_CUDA      = -5,
+    B200SA_ERR_INTERNAL  = -6   /* device-side invariant violated                 */
+};
+
+/* Context: binds a CUDA device, one stream, the device workspace. */
+int  b200sa_ctx_create(int device, b200sa_ctx **out);
+void b200sa_ctx_destroy(b200sa_ctx *ctx);
+
+/* ---- host-buffer entry points (what a Rust/C++ SuffixTable binds) ---- */
+
+/* Replaces `sais_table(text) -> Vec<u32>` (src/table.rs:378-386), the body of
+ * SuffixTable::new (src/table.rs:78-85).  text: n bytes (any bytes; UTF-8 is
+ * handled at byte level exactly like the reference's `Utf8` wrapper,
+ * src/table.rs:778-800).  sa_out: n u32, caller-allocated.  n==0 and n==1
+ * succeed without launching (src/table.rs:395-402). */
+int b200sa_build(b200sa_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t *sa_out);
+
+/* Replaces `lcp_lens_quadratic(text, table) -> Vec<u32>` (src/table.rs:348-361)
+ * as called by SuffixTable::lcp_lens (src/table.rs:130-138):
+ * lcp[0]=0, lcp[i]=|common byte prefix of suffix sa[i-1], suffix sa[i]|. */
+int b200sa_lcp(b200sa_ctx *ctx, const uint8_t *text, uint64_t n,
+               const uint32_t *sa, uint32_t *lcp_out);
+
+/* new + lcp_lens in one call; text and SA stay device-resident in between. */
+int b200sa_build_lcp(b200sa_ctx *ctx, const uint8_t *text, uint64_t n,
+                     uint32_t *sa_out, uint32_t *lcp_out);
+
+/* ---- device-resident twins (PCIe-free; used by bench.py's `value`) ----
+ * d_* are device pointers on the context's device; `stream` is a
+ * cudaStream_t (NULL = the context's own stream).  The calls enqueue work and
+ * synchronise the stream only where the pipeline must read sizes back. */
+int b200sa_build_dev(b200sa_ctx *ctx, const uint8_t *d_text, uint64_t n,
+                     uint32_t *d_sa, void *stream);
+int b200sa_lcp_dev(b200sa_ctx *ctx, const uint8_t *d_text, uint64_t n,
+                   const uint32_t *d_sa, uint32_t *d_lcp, void *stream);
+
+/* ---- batched queries over a device-resident index ----
+ * Replaces SuffixTable::positions (src/table.rs:223-259) for a batch: query q
+ * is bytes [q_off[q], q_off[q+1]) of d_queries; writes the SA range
+ * [start[q], end[q]) whose entries are the match positions (SA order, as the
+ * reference returns them). */
+int b200sa_positions_dev(b200sa_ctx *ctx, const uint8_t *d_text, uint64_t n,
+                         const uint32_t *d_sa, const uint8_t *d_queries,
+                         const uint64_t *d_q_off, uint32_t nq,
+                         uint32_t *d_start, uint32_t *d_end, void *stream);
+
+/* ---- introspection (bench / tests) ---- */
+
+typedef struct {
+    uint64_t n;               /* text bytes of the last build                     */
+    uint64_t m;               /* LMS suffixes at level 0                          */
+    uint64_t names;           /* distinct LMS substrings (reduced alphabet)       */
+    uint32_t doubling_rounds; /* rank-pair doubling rounds on the reduced string  */
+    uint32_t kernel_launches; /* kernels launched by the last call                */
+    uint32_t induce_blocks;   /* grid of the persistent induce kernels            */
+    uint32_t sm_count;
+    uint64_t workspace_bytes; /* device workspace currently held                  */
+} b200sa_stats;
+
+int b200sa_last_stats(b200sa_ctx *ctx, b200sa_stats *out);
+
+/* Per-phase device times (CUDA events on the launching stream) of the last
+ * call.  Enable with b200sa_set_timing(ctx, 1).  Returns the number of phases;
+ * fills up to cap entries.  names[i] points to static strings. */
+int b200sa_set_timing(b200sa_ctx *ctx, int enabled);
+int b200sa_last_phase_times(b200sa_ctx *ctx, const char **names, float *ms, int cap);
+
+const char *b200sa_strerror(int code);
+const char *b200sa_last_error(b200sa_ctx *ctx);   /* detail of the last failure */
+const char *b200sa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SA_H */

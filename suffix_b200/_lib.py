@@ -1,0 +1,157 @@
+"""ctypes loader for libb200sa.so.  There is no CPU fallback: if the CUDA
+library is missing or no device is usable, every call raises."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200sa.so")
+
+
+class B200SAError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__("b200sa error %d (%s)%s" % (code, strerror(code), (": " + detail) if detail else ""))
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_uint64), ("m", ctypes.c_uint64), ("names", ctypes.c_uint64),
+                ("doubling_rounds", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32),
+                ("induce_blocks", ctypes.c_uint32), ("sm_count", ctypes.c_uint32),
+                ("workspace_bytes", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libb200sa.so (built by __graft_entry__.build()); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libb200sa.so is not built (run `python __graft_entry__.py`); "
+                           "suffix_b200 has no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u64, u32, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+    sig = {
+        "b200sa_ctx_create": ([ci, ctypes.POINTER(vp)], ci),
+        "b200sa_ctx_destroy": ([vp], None),
+        "b200sa_build": ([vp, vp, u64, vp], ci),
+        "b200sa_lcp": ([vp, vp, u64, vp, vp], ci),
+        "b200sa_build_lcp": ([vp, vp, u64, vp, vp], ci),
+        "b200sa_build_dev": ([vp, vp, u64, vp, vp], ci),
+        "b200sa_lcp_dev": ([vp, vp, u64, vp, vp, vp], ci),
+        "b200sa_positions_dev": ([vp, vp, u64, vp, vp, vp, u32, vp, vp, vp], ci),
+        "b200sa_last_stats": ([vp, ctypes.POINTER(Stats)], ci),
+        "b200sa_set_timing": ([vp, ci], ci),
+        "b200sa_last_phase_times": ([vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ci], ci),
+        "b200sa_strerror": ([ci], ctypes.c_char_p),
+        "b200sa_last_error": ([vp], ctypes.c_char_p),
+        "b200sa_version": ([], ctypes.c_char_p),
+        "b200sa_test_classify": ([vp, vp, u64, vp, vp, vp, vp, u64, ctypes.POINTER(u64)], ci),
+        "b200sa_test_scan": ([vp, vp, u64, ci, vp, ctypes.POINTER(u32)], ci),
+        "b200sa_test_sort_pairs32": ([vp, vp, vp, u64, ci], ci),
+        "b200sa_test_sort_pairs64": ([vp, vp, vp, u64, ci], ci),
+        "b200sa_test_reduced_sa": ([vp, vp, u64, u32, vp, ctypes.POINTER(u32)], ci),
+        "b200sa_debug_fetch": ([vp, ci, vp, u64], ctypes.c_int64),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+def strerror(code):
+    try:
+        return lib().b200sa_strerror(code).decode()
+    except Exception:
+        return "?"
+
+
+class Context:
+    """One CUDA device + stream + reusable device workspace (b200sa_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        rc = lib().b200sa_ctx_create(device, ctypes.byref(self._h))
+        if rc != 0:
+            raise B200SAError(rc, "b200sa_ctx_create(device=%d)" % device)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().b200sa_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200SAError(rc, lib().b200sa_last_error(self._h).decode())
+
+    # ---- host-buffer API
+    def build(self, text: np.ndarray) -> np.ndarray:
+        sa = np.empty(len(text), dtype=np.uint32)
+        self._check(lib().b200sa_build(self._h, text.ctypes.data, len(text), sa.ctypes.data))
+        return sa
+
+    def lcp(self, text: np.ndarray, sa: np.ndarray) -> np.ndarray:
+        out = np.empty(len(text), dtype=np.uint32)
+        self._check(lib().b200sa_lcp(self._h, text.ctypes.data, len(text), sa.ctypes.data, out.ctypes.data))
+        return out
+
+    def build_lcp(self, text: np.ndarray):
+        sa = np.empty(len(text), dtype=np.uint32)
+        lcp = np.empty(len(text), dtype=np.uint32)
+        self._check(lib().b200sa_build_lcp(self._h, text.ctypes.data, len(text), sa.ctypes.data, lcp.ctypes.data))
+        return sa, lcp
+
+    # ---- device-pointer API (raw integer device pointers, e.g. torch .data_ptr())
+    def build_dev(self, d_text: int, n: int, d_sa: int, stream: int = 0):
+        self._check(lib().b200sa_build_dev(self._h, d_text, n, d_sa, stream))
+
+    def lcp_dev(self, d_text: int, n: int, d_sa: int, d_lcp: int, stream: int = 0):
+        self._check(lib().b200sa_lcp_dev(self._h, d_text, n, d_sa, d_lcp, stream))
+
+    def positions_dev(self, d_text, n, d_sa, d_q, d_qoff, nq, d_start, d_end, stream: int = 0):
+        self._check(lib().b200sa_positions_dev(self._h, d_text, n, d_sa, d_q, d_qoff, nq, d_start, d_end, stream))
+
+    # ---- introspection
+    def set_timing(self, on: bool):
+        self._check(lib().b200sa_set_timing(self._h, 1 if on else 0))
+
+    def phase_times(self):
+        names = (ctypes.c_char_p * 64)()
+        ms = (ctypes.c_float * 64)()
+        k = lib().b200sa_last_phase_times(self._h, names, ms, 64)
+        return [(names[i].decode(), float(ms[i])) for i in range(max(0, min(k, 64)))]
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(lib().b200sa_last_stats(self._h, ctypes.byref(s)))
+        return {f: int(getattr(s, f)) for f, _ in Stats._fields_}
+
+    def debug_fetch(self, which: int, cap: int = 1 << 26) -> np.ndarray:
+        out = np.empty(cap, dtype=np.uint32)
+        k = lib().b200sa_debug_fetch(self._h, which, out.ctypes.data, cap)
+        if k < 0:
+            raise B200SAError(int(k))
+        return out[:min(k, cap)].copy()
+
+
+_default = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """Lazily created per-device context used by SuffixTable."""
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]

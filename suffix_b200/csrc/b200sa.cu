@@ -1,0 +1,682 @@
+// b200sa.cu -- context, level driver and C-ABI of libb200sa.so (sm_100a).
+//
+// Host-side level driver for the device pipeline that replaces
+// `sais_table` / `sais` (reference src/table.rs:378-574) and
+// `lcp_lens_quadratic` (src/table.rs:348-361).  See DESIGN.md for the phase
+// map.  No CPU fallback exists: every entry point launches CUDA kernels or
+// fails with an error code.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200sa.h"
+#include "../../include/b200sa_internal.h"
+#include "common.cuh"
+#include "classify.cuh"
+#include "induce.cuh"
+#include "pipeline_kernels.cuh"
+
+using namespace b200sa;
+
+// ---------------------------------------------------------------- context
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct b200sa_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;   // stream of the current call
+    int sm_count = 0;
+    int induce_blocks = 0;
+    std::string last_error;
+    bool timing = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    std::vector<const char *> phase_names;
+    std::vector<float> phase_ms;
+    b200sa_stats stats;
+    uint32_t launches = 0;
+    uint32_t *h_pin = nullptr;       // pinned read-back area (64 words)
+    size_t ws_bytes = 0;
+    // ---- workspace
+    DevBuf text, sa, lcp;                      // staging for the host API
+    DevBuf pred, stype, lmsb, lmsrank, lmspos, lmslist, lmspred, sorted, flag, reduced, sa_r;
+    DevBuf blkstate, carry, tables, small, scan_partial, radix_cnt, blkcnt;
+    DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
+    uint64_t last_n = 0, last_m = 0;
+};
+
+static const char *kVersion = "b200sa 0.1 (sm_100a)";
+
+#define CU_TRY(ctx, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            char buf__[512];                                                                \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,     \
+                     cudaGetErrorString(e__));                                              \
+            (ctx)->last_error = buf__;                                                      \
+            return (e__ == cudaErrorMemoryAllocation) ? B200SA_ERR_OOM : B200SA_ERR_CUDA;   \
+        }                                                                                   \
+    } while (0)
+
+#define TRY(expr)                        \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != B200SA_OK) return rc__; \
+    } while (0)
+
+static int ensure(b200sa_ctx *c, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return B200SA_OK;
+    if (b.p) { CU_TRY(c, cudaFree(b.p)); c->ws_bytes -= b.cap; b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 16 + 256;    // a little slack against regrowth
+    want = (want + 255) & ~(size_t)255;
+    CU_TRY(c, cudaMalloc(&b.p, want));
+    b.cap = want;
+    c->ws_bytes += want;
+    return B200SA_OK;
+}
+template <class T>
+static T *ptr(DevBuf &b) { return reinterpret_cast<T *>(b.p); }
+
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+static int mark(b200sa_ctx *c, const char *name) {
+    if (!c->timing) return B200SA_OK;
+    if (c->events_used == c->event_pool.size()) {
+        cudaEvent_t e;
+        CU_TRY(c, cudaEventCreate(&e));
+        c->event_pool.push_back(e);
+    }
+    cudaEvent_t e = c->event_pool[c->events_used++];
+    CU_TRY(c, cudaEventRecord(e, c->stream));
+    c->marks.push_back({name, e});
+    return B200SA_OK;
+}
+static void begin_call(b200sa_ctx *c, void *stream) {
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    c->marks.clear();
+    c->events_used = 0;
+    c->launches = 0;
+    c->last_error.clear();
+}
+static int end_call(b200sa_ctx *c) {
+    c->stats.kernel_launches = c->launches;
+    c->stats.workspace_bytes = c->ws_bytes;
+    c->phase_names.clear();
+    c->phase_ms.clear();
+    if (c->timing && c->marks.size() >= 2) {
+        CU_TRY(c, cudaEventSynchronize(c->marks.back().second));
+        for (size_t i = 0; i + 1 < c->marks.size(); i++) {
+            float ms = 0;
+            CU_TRY(c, cudaEventElapsedTime(&ms, c->marks[i].second, c->marks[i + 1].second));
+            c->phase_names.push_back(c->marks[i].first);
+            c->phase_ms.push_back(ms);
+        }
+    }
+    return B200SA_OK;
+}
+
+template <class... KArgs, class... Args>
+static inline void launch_k(b200sa_ctx *c, void (*kern)(KArgs...), uint32_t grid, Args... args) {
+    kern<<<grid, BLK, 0, c->stream>>>(args...);
+    c->launches++;
+}
+#define LAUNCH(ctx, kern, grid, ...) launch_k((ctx), kern, (grid), __VA_ARGS__)
+
+static int read_words(b200sa_ctx *c, const uint32_t *dsrc, int count) {
+    CU_TRY(c, cudaMemcpyAsync(c->h_pin, dsrc, sizeof(uint32_t) * count, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return B200SA_OK;
+}
+
+// ------------------------------------------------------- generic primitives
+template <class Op, class InF, class OutF>
+static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, uint32_t *d_total) {
+    if (n == 0) {
+        if (d_total) CU_TRY(c, cudaMemsetAsync(d_total, 0, 4, c->stream));
+        return B200SA_OK;
+    }
+    uint32_t nb = cdiv(n, SCAN_CHUNK);
+    TRY(ensure(c, c->scan_partial, (size_t)nb * 4));
+    uint32_t *part = ptr<uint32_t>(c->scan_partial);
+    LAUNCH(c, (k_scan_reduce<Op, InF>), nb, in, n, part);
+    LAUNCH(c, (k_scan_partials<Op>), 1, part, nb, d_total);
+    LAUNCH(c, (k_scan_apply<Op, InF, OutF>), nb, in, out, n, part);
+    CU_TRY(c, cudaGetLastError());
+    return B200SA_OK;
+}
+
+constexpr uint32_t MAX_RADIX_BLOCKS = 1184;   // 148 SMs x 8
+
+template <class DigF, class MoveF>
+static int radix_pass(b200sa_ctx *c, DigF dig, MoveF mv, uint64_t n) {
+    if (n == 0) return B200SA_OK;
+    uint32_t tiles = cdiv(n, TILE);
+    uint32_t nb = tiles < MAX_RADIX_BLOCKS ? tiles : MAX_RADIX_BLOCKS;
+    uint32_t tpb = cdiv(tiles, nb);
+    nb = cdiv(tiles, tpb);
+    TRY(ensure(c, c->radix_cnt, (size_t)256 * nb * 4));
+    uint32_t *cnt = ptr<uint32_t>(c->radix_cnt);
+    LAUNCH(c, (k_radix_hist<DigF>), nb, dig, n, tpb, cnt);
+    TRY((dev_scan<OpSum>(c, InArray{cnt}, OutStoreExcl{cnt}, (uint64_t)256 * nb, nullptr)));
+    LAUNCH(c, (k_radix_scatter<DigF, MoveF>), nb, dig, mv, n, tpb, cnt);
+    CU_TRY(c, cudaGetLastError());
+    return B200SA_OK;
+}
+
+// Sorts (ka,va) by the low `bits` of the key; *kout/*vout point at the buffer
+// pair holding the result.
+template <class K>
+static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, uint64_t n, int bits,
+                      K **kout, uint32_t **vout) {
+    for (int shift = 0; shift < bits; shift += 8) {
+        TRY(radix_pass(c, DigKey<K>{ka, (uint32_t)shift}, MoveKV<K>{ka, va, kb, vb}, n));
+        K *tk = ka; ka = kb; kb = tk;
+        uint32_t *tv = va; va = vb; vb = tv;
+    }
+    *kout = ka;
+    *vout = va;
+    return B200SA_OK;
+}
+
+static int bit_length(uint64_t x) {
+    int b = 0;
+    while (x) { b++; x >>= 1; }
+    return b;
+}
+
+// ------------------------------------------------------- reduced problem
+// SA of the u32 string R[0..m) (all symbols < names) -> ctx->sa_r.
+// Stands in for the reference's recursion (src/table.rs:494-500): sort by
+// name, then refine (group, rank[i+h]) pairs, doubling h, keeping only
+// suffixes whose group is not yet a singleton.
+static int reduced_sa(b200sa_ctx *c, uint32_t *R, uint32_t m, uint32_t names, uint32_t *rounds_out) {
+    TRY(ensure(c, c->sa_r, (size_t)m * 4));
+    TRY(ensure(c, c->k32b, (size_t)m * 4));
+    TRY(ensure(c, c->v0, (size_t)m * 4));
+    TRY(ensure(c, c->v1, (size_t)m * 4));
+    TRY(ensure(c, c->p0, (size_t)m * 4));
+    TRY(ensure(c, c->p1, (size_t)m * 4));
+    TRY(ensure(c, c->g0, (size_t)m * 4));
+    TRY(ensure(c, c->g1, (size_t)m * 4));
+    TRY(ensure(c, c->rank, (size_t)m * 4));
+    TRY(ensure(c, c->small, 256));
+    uint32_t *sa_r = ptr<uint32_t>(c->sa_r), *rank = ptr<uint32_t>(c->rank);
+    uint32_t *V0 = ptr<uint32_t>(c->v0), *V1 = ptr<uint32_t>(c->v1);
+    uint32_t *P0 = ptr<uint32_t>(c->p0), *P1 = ptr<uint32_t>(c->p1);
+    uint32_t *G0 = ptr<uint32_t>(c->g0), *G1 = ptr<uint32_t>(c->g1);
+    uint32_t *d_na = ptr<uint32_t>(c->small);
+    uint32_t rounds = 0;
+
+    // round 0: sort suffixes by first symbol
+    LAUNCH(c, k_iota, cdiv(m, BLK), V0, m);
+    uint32_t *Ks, *Vs;
+    int bits0 = bit_length(names > 0 ? names - 1 : 0);
+    if (bits0 < 1) bits0 = 1;
+    TRY(sort_pairs<uint32_t>(c, R, V0, ptr<uint32_t>(c->k32b), V1, m, bits0, &Ks, &Vs));
+    TRY((dev_scan<OpMax>(c, InGroupStart<uint32_t>{Ks, nullptr}, OutGroupRank{Vs, nullptr, G1, rank, sa_r}, m, nullptr)));
+    uint32_t *Vfree = (Vs == V0) ? V1 : V0;
+    TRY((dev_scan<OpSum>(c, InActive<uint32_t>{Ks, m}, OutCompactActive{nullptr, Vs, G1, P0, Vfree, G0}, m, d_na)));
+    TRY(read_words(c, d_na, 1));
+    uint32_t na = c->h_pin[0];
+    uint32_t *asuf = Vfree, *ascratch = Vs, *apos = P0, *apos_next = P1, *agrp = G0;
+    if (na > 0) {
+        TRY(ensure(c, c->k64a, (size_t)na * 8));
+        TRY(ensure(c, c->k64b, (size_t)na * 8));
+    }
+    int b2 = bit_length(m);
+    uint64_t h = 1;
+    while (na > 0) {
+        rounds++;
+        if (rounds > 40) { c->last_error = "doubling did not converge"; return B200SA_ERR_INTERNAL; }
+        uint64_t *KA = ptr<uint64_t>(c->k64a), *KB = ptr<uint64_t>(c->k64b), *K2;
+        uint32_t hh = h > 0xffffffffull ? 0xffffffffu : (uint32_t)h;
+        LAUNCH(c, k_pair_keys, cdiv(na, BLK), agrp, asuf, rank, na, m, hh, (uint32_t)b2, KA);
+        uint32_t *Vsorted;
+        TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, 2 * b2, &K2, &Vsorted));
+        uint32_t *Vother = (Vsorted == asuf) ? ascratch : asuf;
+        TRY((dev_scan<OpMax>(c, InGroupStart<uint64_t>{K2, apos}, OutGroupRank{Vsorted, apos, G1, rank, sa_r}, na, nullptr)));
+        TRY((dev_scan<OpSum>(c, InActive<uint64_t>{K2, na}, OutCompactActive{apos, Vsorted, G1, apos_next, Vother, G0}, na, d_na)));
+        TRY(read_words(c, d_na, 1));
+        na = c->h_pin[0];
+        asuf = Vother; ascratch = Vsorted;
+        uint32_t *t = apos; apos = apos_next; apos_next = t;
+        agrp = G0;
+        h *= 2;
+    }
+    if (rounds_out) *rounds_out = rounds;
+    return B200SA_OK;
+}
+
+// ------------------------------------------------------- induce launcher
+static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_t n, uint32_t *sa,
+                         const uint32_t *lms, uint32_t m) {
+    (void)m;
+    uint32_t *tab = ptr<uint32_t>(c->tables);
+    InduceArgs A;
+    A.text = text; A.n = n; A.sa = sa; A.pred = ptr<uint8_t>(c->pred);
+    A.lms = lms; A.lms_pred = ptr<uint8_t>(c->lmspred);
+    A.bstart = tab; A.Lcnt = tab + 257; A.Scnt = tab + 257 + 256; A.lms_off = tab + 257 + 512;
+    A.blk_cnt = ptr<uint32_t>(c->blkcnt);
+    uint32_t *sm = ptr<uint32_t>(c->small);
+    A.g_fill = sm + 64; A.g_state = reinterpret_cast<int32_t *>(sm + 320); A.err = sm + 32;
+    void *args[] = {&A};
+    const void *fn = spass ? (const void *)k_induce<true> : (const void *)k_induce<false>;
+    CU_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(c->induce_blocks), dim3(BLK), args, 0, c->stream));
+    c->launches++;
+    return B200SA_OK;
+}
+
+// ------------------------------------------------------- the level driver
+static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *m_out) {
+    uint64_t nw = (n + 31) / 32;
+    uint32_t nbc = cdiv(nw, CLS_WORDS);
+    TRY(ensure(c, c->stype, nw * 4));
+    TRY(ensure(c, c->lmsb, nw * 4));
+    TRY(ensure(c, c->lmsrank, nw * 4));
+    TRY(ensure(c, c->blkstate, nbc));
+    TRY(ensure(c, c->carry, nbc));
+    TRY(ensure(c, c->tables, (257 + 256 + 256 + 257 + 768) * 4));
+    TRY(ensure(c, c->small, 4096));
+    uint32_t *tab = ptr<uint32_t>(c->tables);
+    uint32_t *hist = tab + 257 + 512 + 257;
+    uint32_t *sm = ptr<uint32_t>(c->small);
+    CU_TRY(c, cudaMemsetAsync(hist, 0, 768 * 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(sm, 0, 4096, c->stream));
+    LAUNCH(c, k_cls_block_state, nbc, text, n, ptr<uint8_t>(c->blkstate));
+    LAUNCH(c, k_cls_carry, 1, ptr<uint8_t>(c->blkstate), nbc, ptr<uint8_t>(c->carry));
+    LAUNCH(c, k_cls_types, nbc, text, n, ptr<uint8_t>(c->carry), ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb), hist);
+    LAUNCH(c, k_bucket_tables, 1, hist, tab, tab + 257, tab + 257 + 256, tab + 257 + 512);
+    CU_TRY(c, cudaGetLastError());
+    TRY((dev_scan<OpSum>(c, InPopcWords{ptr<uint32_t>(c->lmsb)}, OutStoreExcl{ptr<uint32_t>(c->lmsrank)}, nw, sm)));
+    TRY(read_words(c, sm, 1));
+    uint32_t m = c->h_pin[0];
+    TRY(ensure(c, c->lmspos, (size_t)m * 4));
+    if (m > 0) {
+        LAUNCH(c, k_lms_positions, cdiv(nw, BLK), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank), nw, ptr<uint32_t>(c->lmspos));
+        CU_TRY(c, cudaGetLastError());
+    }
+    *m_out = m;
+    return B200SA_OK;
+}
+
+static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t *d_sa) {
+    memset(&c->stats, 0, sizeof c->stats);
+    c->stats.n = n;
+    c->stats.sm_count = c->sm_count;
+    c->stats.induce_blocks = c->induce_blocks;
+    c->last_n = n; c->last_m = 0;
+    if (n > 0xFFFFFFFFull) { c->last_error = "text longer than 2^32-1 bytes"; return B200SA_ERR_TOO_LARGE; }
+    if (n == 0) return B200SA_OK;
+    if (n == 1) { CU_TRY(c, cudaMemsetAsync(d_sa, 0, 4, c->stream)); return B200SA_OK; }
+    const uint8_t *text = d_text;
+    if (((uintptr_t)d_text & 15) != 0) {       // vector loads need 16-byte alignment
+        TRY(ensure(c, c->text, n));
+        CU_TRY(c, cudaMemcpyAsync(c->text.p, d_text, n, cudaMemcpyDeviceToDevice, c->stream));
+        text = ptr<uint8_t>(c->text);
+    }
+    uint32_t n32 = (uint32_t)n;
+    TRY(mark(c, "classify"));
+    uint32_t m = 0;
+    TRY(classify_dev(c, text, n, &m));
+    c->stats.m = m; c->last_m = m;
+    TRY(ensure(c, c->pred, n));
+    TRY(ensure(c, c->lmslist, (size_t)m * 4));
+    TRY(ensure(c, c->lmspred, m));
+    TRY(ensure(c, c->blkcnt, (size_t)2 * c->induce_blocks * 256 * 4));
+    uint32_t *lmslist = ptr<uint32_t>(c->lmslist);
+    if (m > 0) {
+        TRY(ensure(c, c->sorted, (size_t)m * 4));
+        TRY(ensure(c, c->flag, m));
+        TRY(ensure(c, c->reduced, (size_t)m * 4));
+        uint32_t *sm = ptr<uint32_t>(c->small);
+        // K3: LMS suffixes grouped by first byte (stable, text order inside a group)
+        TRY(mark(c, "lms_group"));
+        TRY(radix_pass(c, DigTextAtPos{text, ptr<uint32_t>(c->lmspos)}, MoveU32{ptr<uint32_t>(c->lmspos), lmslist}, m));
+        // stage 1: induced sort of the LMS substrings
+        TRY(mark(c, "induce1_L"));
+        TRY(launch_induce(c, false, text, n32, d_sa, lmslist, m));
+        TRY(mark(c, "induce1_S"));
+        TRY(launch_induce(c, true, text, n32, d_sa, lmslist, m));
+        // K6: sorted LMS substrings
+        TRY(mark(c, "compact_lms"));
+        TRY((dev_scan<OpSum>(c, InIsLmsEntry{d_sa, ptr<uint32_t>(c->lmsb)}, OutCompactSa{d_sa, ptr<uint32_t>(c->sorted)}, n, sm + 1)));
+        // K7/K8: names, reduced string
+        TRY(mark(c, "name"));
+        LAUNCH(c, k_name_flags, cdiv(m, BLK), text, n32, ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb),
+               ptr<uint32_t>(c->sorted), m, ptr<uint8_t>(c->flag));
+        TRY((dev_scan<OpSum>(c, InFlagU8{ptr<uint8_t>(c->flag)},
+                             OutReduced{ptr<uint32_t>(c->sorted), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank), ptr<uint32_t>(c->reduced)},
+                             m, sm + 2)));
+        TRY(read_words(c, sm + 1, 2));
+        uint32_t cnt_lms = c->h_pin[0], names = c->h_pin[1];
+        if (cnt_lms != m) {
+            char b[160]; snprintf(b, sizeof b, "stage-1 induce lost LMS entries: %u of %u", cnt_lms, m);
+            c->last_error = b; return B200SA_ERR_INTERNAL;
+        }
+        c->stats.names = names;
+        TRY(mark(c, "reduced_sa"));
+        TRY(ensure(c, c->sa_r, (size_t)m * 4));
+        if (names == m) {
+            LAUNCH(c, k_invert_perm, cdiv(m, BLK), ptr<uint32_t>(c->reduced), m, ptr<uint32_t>(c->sa_r));
+        } else {
+            uint32_t rounds = 0;
+            TRY(reduced_sa(c, ptr<uint32_t>(c->reduced), m, names, &rounds));
+            c->stats.doubling_rounds = rounds;
+        }
+        // K10: ranks -> text positions; the list is grouped by first byte by construction
+        TRY(mark(c, "unrename"));
+        LAUNCH(c, k_unrename, cdiv(m, BLK), ptr<uint32_t>(c->sa_r), ptr<uint32_t>(c->lmspos), m, lmslist);
+        CU_TRY(c, cudaGetLastError());
+    }
+    // stage 2: final induce from the sorted LMS suffixes
+    TRY(mark(c, "induce2_L"));
+    TRY(launch_induce(c, false, text, n32, d_sa, lmslist, m));
+    TRY(mark(c, "induce2_S"));
+    TRY(launch_induce(c, true, text, n32, d_sa, lmslist, m));
+    TRY(mark(c, "end"));
+    TRY(read_words(c, ptr<uint32_t>(c->small) + 32, 4));
+    if (c->h_pin[0] != 0) {
+        char b[200];
+        snprintf(b, sizeof b, "induce invariant violated: bucket %u filled %u, expected %u", c->h_pin[1], c->h_pin[2], c->h_pin[3]);
+        c->last_error = b;
+        return B200SA_ERR_INTERNAL;
+    }
+    return B200SA_OK;
+}
+
+static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa, uint32_t *d_lcp) {
+    if (n > 0xFFFFFFFFull) return B200SA_ERR_TOO_LARGE;
+    if (n == 0) return B200SA_OK;
+    uint32_t n32 = (uint32_t)n;
+    TRY(ensure(c, c->isa, (size_t)n * 4));
+    TRY(mark(c, "lcp_isa"));
+    LAUNCH(c, k_isa, cdiv(n, BLK), d_sa, n32, ptr<uint32_t>(c->isa));
+    TRY(mark(c, "lcp_kasai"));
+    LAUNCH(c, k_lcp_kasai, cdiv(cdiv(n, LCP_CHUNK), BLK), d_text, n32, d_sa, ptr<uint32_t>(c->isa), d_lcp);
+    TRY(mark(c, "end"));
+    CU_TRY(c, cudaGetLastError());
+    return B200SA_OK;
+}
+
+template <class K>
+static int test_sort(b200sa_ctx *c, K *keys, uint32_t *vals, uint64_t n, int bits) {
+    if (!c || (n > 0 && (!keys || !vals))) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, nullptr);
+    TRY(ensure(c, c->k64a, n * sizeof(K)));
+    TRY(ensure(c, c->k64b, n * sizeof(K)));
+    TRY(ensure(c, c->v0, n * 4));
+    TRY(ensure(c, c->v1, n * 4));
+    CU_TRY(c, cudaMemcpyAsync(c->k64a.p, keys, n * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->v0.p, vals, n * 4, cudaMemcpyHostToDevice, c->stream));
+    K *ko; uint32_t *vo;
+    TRY(sort_pairs<K>(c, ptr<K>(c->k64a), ptr<uint32_t>(c->v0), ptr<K>(c->k64b), ptr<uint32_t>(c->v1), n, bits, &ko, &vo));
+    if (n) {
+        CU_TRY(c, cudaMemcpyAsync(keys, ko, n * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(vals, vo, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return end_call(c);
+}
+
+// ================================================================= C ABI
+extern "C" {
+
+const char *b200sa_version(void) { return kVersion; }
+
+const char *b200sa_strerror(int code) {
+    switch (code) {
+        case B200SA_OK: return "ok";
+        case B200SA_ERR_BAD_ARG: return "bad argument";
+        case B200SA_ERR_TOO_LARGE: return "text longer than 2^32-1 bytes";
+        case B200SA_ERR_NO_DEVICE: return "no usable CUDA device";
+        case B200SA_ERR_OOM: return "out of device memory";
+        case B200SA_ERR_CUDA: return "CUDA error";
+        case B200SA_ERR_INTERNAL: return "internal invariant violated";
+        default: return "unknown error";
+    }
+}
+
+const char *b200sa_last_error(b200sa_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int b200sa_ctx_create(int device, b200sa_ctx **out) {
+    if (!out) return B200SA_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return B200SA_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return B200SA_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return B200SA_ERR_NO_DEVICE;
+    b200sa_ctx *c = new b200sa_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
+    c->sm_count = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) { delete c; return B200SA_ERR_NO_DEVICE; }
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
+    c->stream = c->own_stream;
+    if (cudaMallocHost((void **)&c->h_pin, 64 * sizeof(uint32_t)) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
+    int occL = 0, occS = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occL, k_induce<false>, BLK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_induce<true>, BLK, 0);
+    int occ = occL < occS ? occL : occS;
+    if (occ < 1) { cudaFreeHost(c->h_pin); delete c; return B200SA_ERR_CUDA; }
+    int bps = 2;
+    if (const char *e = getenv("B200SA_INDUCE_BPS")) { int v = atoi(e); if (v >= 1) bps = v; }
+    if (bps > occ) bps = occ;
+    c->induce_blocks = c->sm_count * bps;
+    memset(&c->stats, 0, sizeof c->stats);
+    *out = c;
+    return B200SA_OK;
+}
+
+void b200sa_ctx_destroy(b200sa_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf *bufs[] = {&c->text, &c->sa, &c->lcp, &c->pred, &c->stype, &c->lmsb, &c->lmsrank, &c->lmspos, &c->lmslist,
+                      &c->lmspred, &c->sorted, &c->flag, &c->reduced, &c->sa_r, &c->blkstate, &c->carry, &c->tables,
+                      &c->small, &c->scan_partial, &c->radix_cnt, &c->blkcnt, &c->k32b, &c->k64a, &c->k64b, &c->v0,
+                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int b200sa_set_timing(b200sa_ctx *c, int enabled) {
+    if (!c) return B200SA_ERR_BAD_ARG;
+    c->timing = enabled != 0;
+    return B200SA_OK;
+}
+
+int b200sa_last_phase_times(b200sa_ctx *c, const char **names, float *ms, int cap) {
+    if (!c) return B200SA_ERR_BAD_ARG;
+    int k = (int)c->phase_names.size();
+    for (int i = 0; i < k && i < cap; i++) {
+        if (names) names[i] = c->phase_names[i];
+        if (ms) ms[i] = c->phase_ms[i];
+    }
+    return k;
+}
+
+int b200sa_last_stats(b200sa_ctx *c, b200sa_stats *out) {
+    if (!c || !out) return B200SA_ERR_BAD_ARG;
+    *out = c->stats;
+    out->workspace_bytes = c->ws_bytes;
+    return B200SA_OK;
+}
+
+int b200sa_build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t *d_sa, void *stream) {
+    if (!c || (n > 0 && (!d_text || !d_sa))) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    int rc = build_dev(c, d_text, n, d_sa);
+    if (rc == B200SA_OK) rc = end_call(c);
+    return rc;
+}
+
+int b200sa_lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa, uint32_t *d_lcp,
+                   void *stream) {
+    if (!c || (n > 0 && (!d_text || !d_sa || !d_lcp))) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    int rc = lcp_dev(c, d_text, n, d_sa, d_lcp);
+    if (rc == B200SA_OK) rc = end_call(c);
+    return rc;
+}
+
+static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *sa_out, uint32_t *lcp_out,
+                      const uint32_t *sa_in) {
+    if (n > 0xFFFFFFFFull) { c->last_error = "text longer than 2^32-1 bytes"; return B200SA_ERR_TOO_LARGE; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, nullptr);
+    memset(&c->stats, 0, sizeof c->stats);
+    c->stats.n = n;
+    if (n == 0) return end_call(c);
+    TRY(ensure(c, c->text, n));
+    TRY(ensure(c, c->sa, (size_t)n * 4));
+    TRY(mark(c, "h2d"));
+    CU_TRY(c, cudaMemcpyAsync(c->text.p, text, n, cudaMemcpyHostToDevice, c->stream));
+    if (sa_in) CU_TRY(c, cudaMemcpyAsync(c->sa.p, sa_in, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (!sa_in) {
+        TRY(build_dev(c, ptr<uint8_t>(c->text), n, ptr<uint32_t>(c->sa)));
+        if (sa_out) {
+            TRY(mark(c, "d2h_sa"));
+            CU_TRY(c, cudaMemcpyAsync(sa_out, c->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    if (lcp_out) {
+        TRY(ensure(c, c->lcp, (size_t)n * 4));
+        TRY(lcp_dev(c, ptr<uint8_t>(c->text), n, ptr<uint32_t>(c->sa), ptr<uint32_t>(c->lcp)));
+        TRY(mark(c, "d2h_lcp"));
+        CU_TRY(c, cudaMemcpyAsync(lcp_out, c->lcp.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    TRY(mark(c, "end"));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return end_call(c);
+}
+
+int b200sa_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *sa_out) {
+    if (!c || (n > 0 && (!text || !sa_out))) return B200SA_ERR_BAD_ARG;
+    return host_build(c, text, n, sa_out, nullptr, nullptr);
+}
+
+int b200sa_lcp(b200sa_ctx *c, const uint8_t *text, uint64_t n, const uint32_t *sa, uint32_t *lcp_out) {
+    if (!c || (n > 0 && (!text || !sa || !lcp_out))) return B200SA_ERR_BAD_ARG;
+    return host_build(c, text, n, nullptr, lcp_out, sa);
+}
+
+int b200sa_build_lcp(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *sa_out, uint32_t *lcp_out) {
+    if (!c || (n > 0 && (!text || !sa_out || !lcp_out))) return B200SA_ERR_BAD_ARG;
+    return host_build(c, text, n, sa_out, lcp_out, nullptr);
+}
+
+int b200sa_positions_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa,
+                         const uint8_t *d_queries, const uint64_t *d_q_off, uint32_t nq, uint32_t *d_start,
+                         uint32_t *d_end, void *stream) {
+    if (!c || (nq > 0 && (!d_q_off || !d_start || !d_end)) || (n > 0 && (!d_text || !d_sa))) return B200SA_ERR_BAD_ARG;
+    if (n > 0xFFFFFFFFull) return B200SA_ERR_TOO_LARGE;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    if (nq > 0) {
+        LAUNCH(c, k_positions, cdiv(nq, BLK), d_text, (uint32_t)n, d_sa, d_queries, d_q_off, nq, d_start, d_end);
+        CU_TRY(c, cudaGetLastError());
+    }
+    return end_call(c);
+}
+
+// ------------------------------------------------------------ test hooks
+int b200sa_test_classify(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *stype_words, uint32_t *lms_words,
+                         uint32_t *hist768, uint32_t *lmspos, uint64_t cap_lms, uint64_t *m_out) {
+    if (!c || !text || n < 1 || n > 0xFFFFFFFFull) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, nullptr);
+    TRY(ensure(c, c->text, n));
+    CU_TRY(c, cudaMemcpyAsync(c->text.p, text, n, cudaMemcpyHostToDevice, c->stream));
+    uint32_t m = 0;
+    TRY(classify_dev(c, ptr<uint8_t>(c->text), n, &m));
+    uint64_t nw = (n + 31) / 32;
+    if (stype_words) CU_TRY(c, cudaMemcpyAsync(stype_words, c->stype.p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (lms_words) CU_TRY(c, cudaMemcpyAsync(lms_words, c->lmsb.p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (hist768) CU_TRY(c, cudaMemcpyAsync(hist768, ptr<uint32_t>(c->tables) + 257 + 512 + 257, 768 * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (lmspos && m > 0) {
+        uint64_t k = m < cap_lms ? m : cap_lms;
+        CU_TRY(c, cudaMemcpyAsync(lmspos, c->lmspos.p, k * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (m_out) *m_out = m;
+    return end_call(c);
+}
+
+int b200sa_test_scan(b200sa_ctx *c, const uint32_t *in, uint64_t n, int op, uint32_t *out_excl, uint32_t *total) {
+    if (!c || (n > 0 && (!in || !out_excl))) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, nullptr);
+    TRY(ensure(c, c->v0, n * 4));
+    TRY(ensure(c, c->v1, n * 4));
+    TRY(ensure(c, c->small, 4096));
+    CU_TRY(c, cudaMemcpyAsync(c->v0.p, in, n * 4, cudaMemcpyHostToDevice, c->stream));
+    uint32_t *d_tot = ptr<uint32_t>(c->small);
+    if (op == 0) TRY((dev_scan<OpSum>(c, InArray{ptr<uint32_t>(c->v0)}, OutStoreExcl{ptr<uint32_t>(c->v1)}, n, d_tot)));
+    else TRY((dev_scan<OpMax>(c, InArray{ptr<uint32_t>(c->v0)}, OutStoreExcl{ptr<uint32_t>(c->v1)}, n, d_tot)));
+    if (n) CU_TRY(c, cudaMemcpyAsync(out_excl, c->v1.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    TRY(read_words(c, d_tot, 1));
+    if (total) *total = c->h_pin[0];
+    return end_call(c);
+}
+
+int b200sa_test_sort_pairs32(b200sa_ctx *c, uint32_t *keys, uint32_t *vals, uint64_t n, int bits) {
+    return test_sort<uint32_t>(c, keys, vals, n, bits);
+}
+int b200sa_test_sort_pairs64(b200sa_ctx *c, uint64_t *keys, uint32_t *vals, uint64_t n, int bits) {
+    return test_sort<uint64_t>(c, keys, vals, n, bits);
+}
+
+int b200sa_test_reduced_sa(b200sa_ctx *c, const uint32_t *R, uint64_t m, uint32_t names, uint32_t *sa_out,
+                           uint32_t *rounds_out) {
+    if (!c || m < 1 || m > 0x7FFFFFFFull || !R || !sa_out) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, nullptr);
+    TRY(ensure(c, c->reduced, m * 4));
+    CU_TRY(c, cudaMemcpyAsync(c->reduced.p, R, m * 4, cudaMemcpyHostToDevice, c->stream));
+    uint32_t rounds = 0;
+    TRY(reduced_sa(c, ptr<uint32_t>(c->reduced), (uint32_t)m, names, &rounds));
+    CU_TRY(c, cudaMemcpyAsync(sa_out, c->sa_r.p, m * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (rounds_out) *rounds_out = rounds;
+    return end_call(c);
+}
+
+int64_t b200sa_debug_fetch(b200sa_ctx *c, int which, void *out, uint64_t cap) {
+    if (!c || !out) return B200SA_ERR_BAD_ARG;
+    if (cudaSetDevice(c->device) != cudaSuccess) return B200SA_ERR_CUDA;
+    const void *src = nullptr;
+    uint64_t count = 0;
+    switch (which) {
+        case 0: src = c->lmspos.p; count = c->last_m; break;
+        case 1: src = c->sorted.p; count = c->last_m; break;
+        case 2: src = c->reduced.p; count = c->last_m; break;
+        case 3: src = c->sa_r.p; count = c->last_m; break;
+        case 4: src = c->lmslist.p; count = c->last_m; break;
+        case 5: src = c->small.p ? (const void *)(ptr<uint32_t>(c->small) + 32) : nullptr; count = 4; break;
+        case 6: src = c->tables.p; count = 257 + 256 + 256 + 257; break;
+        default: return B200SA_ERR_BAD_ARG;
+    }
+    if (!src) return 0;
+    uint64_t k = count < cap ? count : cap;
+    if (k && cudaMemcpy(out, src, k * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return B200SA_ERR_CUDA;
+    return (int64_t)count;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+// classify.cuh -- K1: S/L type classification, LMS flags, (char,type)
+// histogram; K2: bucket tables.  Replaces SuffixTypes::compute
+// (reference src/table.rs:592-615) and Bins::find_sizes / find_*_pointers
+// (src/table.rs:686-720) for the byte-level text.
+//
+// Layout: position i lives in bit (i & 31) of word (i >> 5).
+//   stype[w]  bit set  <=> position is S-class (Ascending or Valley)
+//   lmsb[w]   bit set  <=> position is a Valley (LMS)
+// Algorithm: rel(i) = cmp(T[i],T[i+1]) (rel(n-1) := L, src/table.rs:602);
+// type(i) = first non-EQ rel(j), j >= i.  One block owns 256 words (8192
+// bytes); pass A reduces each block to {L,S,P(ropagate)}, pass B resolves the
+// carries right-to-left across blocks, pass C materialises the bitmaps and the
+// histogram with the carry known.
+#pragma once
+#include "common.cuh"
+
+namespace b200sa {
+
+constexpr uint32_t ST_L = 0, ST_S = 1, ST_P = 2;
+constexpr int CLS_WORDS = BLK;             // words per block
+constexpr int CLS_BYTES = CLS_WORDS * 32;  // 8192 text bytes per block
+
+// Loads the 32 bytes of word w (zero beyond n) plus the following byte.
+// Returns the number of valid positions in the word.
+__device__ __forceinline__ uint32_t load_word(const uint8_t *__restrict__ text, uint64_t n, uint64_t w,
+                                              uint32_t (&c)[8], uint32_t &nextc, bool &has_next) {
+    uint64_t p0 = w * 32;
+    uint32_t cnt;
+    if (p0 + 32 <= n) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(text + p0);
+        uint4 a = __ldg(q), b = __ldg(q + 1);
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w;
+        c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+        cnt = 32;
+    } else {
+        cnt = (p0 < n) ? (uint32_t)(n - p0) : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            if ((uint32_t)j < cnt) c[j >> 2] |= (uint32_t)__ldg(text + p0 + j) << ((j & 3) * 8);
+    }
+    has_next = (p0 + 32 < n);
+    nextc = has_next ? (uint32_t)__ldg(text + p0 + 32) : 0u;
+    return cnt;
+}
+
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&c)[8], int j) {
+    return (c[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+}
+
+// lt/gt masks of rel(i) for the word's positions; rel(n-1) forced to L.
+__device__ __forceinline__ void word_rel(const uint32_t (&c)[8], uint32_t cnt, uint32_t nextc, bool has_next,
+                                         uint32_t &lt, uint32_t &gt) {
+    lt = 0; gt = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        uint32_t a = byte_of(c, j);
+        uint32_t b = (j < 31) ? byte_of(c, (j + 1) & 31) : nextc;
+        bool valid = (uint32_t)j < cnt;
+        bool last = ((uint32_t)j + 1 == cnt) && !has_next;   // position n-1
+        if (valid) {
+            if (last) gt |= 1u << j;
+            else if (a < b) lt |= 1u << j;
+            else if (a > b) gt |= 1u << j;
+        }
+    }
+}
+
+// "First non-P state among threads with larger index in this block", else
+// ST_P.  mine = this thread's state.  s_warp: NWARP words.
+__device__ __forceinline__ uint32_t first_nonp_right(uint32_t mine, uint32_t *s_warp) {
+    const uint32_t l = lane_id(), w = warp_id();
+    uint32_t nonp = __ballot_sync(FULL, mine != ST_P);
+    uint32_t sb = __ballot_sync(FULL, mine == ST_S);
+    __syncthreads();
+    if (l == 0) s_warp[w] = nonp ? ((sb >> (__ffs(nonp) - 1)) & 1u) : ST_P;   // first non-P of the warp
+    __syncthreads();
+    uint32_t hm = (l == 31) ? 0u : (nonp & ~((2u << l) - 1u));
+    if (hm) return (sb >> (__ffs(hm) - 1)) & 1u;
+    for (uint32_t ww = w + 1; ww < NWARP; ww++) {
+        uint32_t s = s_warp[ww];
+        if (s != ST_P) return s;
+    }
+    return ST_P;
+}
+
+// Pass A: block state = first non-EQ rel in the block's byte range.
+__global__ void __launch_bounds__(BLK) k_cls_block_state(const uint8_t *__restrict__ text, uint64_t n,
+                                                         uint8_t *blk_state) {
+    __shared__ uint32_t s_warp[NWARP];
+    uint64_t w = (uint64_t)blockIdx.x * CLS_WORDS + threadIdx.x;
+    uint32_t c[8], nextc, lt, gt;
+    bool has_next;
+    uint32_t cnt = load_word(text, n, w, c, nextc, has_next);
+    word_rel(c, cnt, nextc, has_next, lt, gt);
+    uint32_t ne = lt | gt;
+    uint32_t mine = ne ? ((lt >> (__ffs(ne) - 1)) & 1u) : ST_P;
+    uint32_t right = first_nonp_right(mine, s_warp);
+    if (threadIdx.x == 0) blk_state[blockIdx.x] = (uint8_t)(mine != ST_P ? mine : right);
+}
+
+// Pass B (single block): carry_in[b] = first non-P state among blocks > b.
+// Walks chunks of 256 block states from the right with a running carry.
+__global__ void __launch_bounds__(BLK) k_cls_carry(const uint8_t *blk_state, uint32_t nb, uint8_t *carry_in) {
+    __shared__ uint32_t s_warp[NWARP];
+    uint32_t carry = ST_L;     // beyond the last block: unused (position n-1 is never EQ)
+    uint32_t nchunks = (nb + BLK - 1) / BLK;
+    for (uint32_t ch = nchunks; ch-- > 0;) {
+        uint32_t b = ch * BLK + threadIdx.x;
+        uint32_t mine = (b < nb) ? blk_state[b] : ST_P;
+        uint32_t right = first_nonp_right(mine, s_warp);
+        if (b < nb) carry_in[b] = (uint8_t)(right != ST_P ? right : carry);
+        // new carry = first non-P of this chunk (thread 0's view including itself)
+        __syncthreads();
+        if (threadIdx.x == 0) s_warp[0] = (mine != ST_P) ? mine : (right != ST_P ? right : carry);
+        __syncthreads();
+        carry = s_warp[0];
+        __syncthreads();
+    }
+}
+
+// Pass C: bitmaps + histogram.  hist768: [0,256) L counts, [256,512) S
+// non-LMS counts, [512,768) LMS counts, per byte value.
+__global__ void __launch_bounds__(BLK) k_cls_types(const uint8_t *__restrict__ text, uint64_t n,
+                                                   const uint8_t *carry_in, uint32_t *stype, uint32_t *lmsb,
+                                                   uint32_t *hist768) {
+    __shared__ uint32_t s_warp[NWARP];
+    __shared__ uint32_t s_sw[BLK];
+    __shared__ uint32_t s_hist[768];
+    for (int k = threadIdx.x; k < 768; k += BLK) s_hist[k] = 0;
+    uint64_t w = (uint64_t)blockIdx.x * CLS_WORDS + threadIdx.x;
+    uint64_t nw = (n + 31) / 32;
+    uint32_t c[8], nextc, lt, gt;
+    bool has_next;
+    uint32_t cnt = load_word(text, n, w, c, nextc, has_next);
+    word_rel(c, cnt, nextc, has_next, lt, gt);
+    uint32_t ne = lt | gt;
+    uint32_t mine = ne ? ((lt >> (__ffs(ne) - 1)) & 1u) : ST_P;
+    uint32_t right = first_nonp_right(mine, s_warp);     // contains __syncthreads (covers s_hist init)
+    uint32_t cin = (right != ST_P) ? right : (uint32_t)carry_in[blockIdx.x];
+    // resolve S bits right-to-left inside the word
+    uint32_t sw = 0, cur = cin;
+#pragma unroll
+    for (int j = 31; j >= 0; j--) {
+        if ((ne >> j) & 1u) cur = (lt >> j) & 1u;
+        sw |= cur << j;
+    }
+    uint32_t vmask = (cnt >= 32) ? 0xffffffffu : ((1u << cnt) - 1u);
+    sw &= vmask;
+    s_sw[threadIdx.x] = sw;
+    __syncthreads();
+    // type bit of the position just before this word
+    uint32_t pb;
+    if (threadIdx.x > 0) pb = s_sw[threadIdx.x - 1] >> 31;
+    else if (w == 0) pb = 1u;                      // position 0 is never a Valley (src/table.rs:465)
+    else if (cnt == 0) pb = 0u;
+    else {
+        uint32_t c1 = __ldg(text + w * 32 - 1), c2 = byte_of(c, 0);
+        pb = (c1 < c2) ? 1u : (c1 > c2) ? 0u : (sw & 1u);
+    }
+    uint32_t lw = sw & ~((sw << 1) | pb);
+    if (w < nw) { stype[w] = sw; lmsb[w] = lw; }
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        bool valid = (uint32_t)j < cnt;
+        uint32_t cls = ((sw >> j) & 1u) + ((lw >> j) & 1u);
+        hist_add(s_hist, byte_of(c, j) + 256u * cls, valid);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 768; k += BLK) {
+        uint32_t v = s_hist[k];
+        if (v) atomicAdd(&hist768[k], v);
+    }
+}
+
+// K2: bucket tables from the histogram (single block).
+//   bstart[c] = start of bucket c in SA (bstart[256] = n)
+//   Lcnt/Scnt = type-split bucket sizes, lms_off = LMS group offsets.
+__global__ void __launch_bounds__(BLK) k_bucket_tables(const uint32_t *hist768, uint32_t *bstart, uint32_t *Lcnt,
+                                                       uint32_t *Scnt, uint32_t *lms_off) {
+    __shared__ uint32_t s_w[NWARP + 1];
+    uint32_t c = threadIdx.x;
+    uint32_t L = hist768[c], S = hist768[256 + c] + hist768[512 + c], M = hist768[512 + c];
+    Lcnt[c] = L; Scnt[c] = S;
+    uint32_t total;
+    uint32_t inc = block_incl_scan<OpSum>(L + S, s_w, &total);
+    bstart[c] = inc - (L + S);
+    if (c == 255) bstart[256] = total;
+    inc = block_incl_scan<OpSum>(M, s_w, &total);
+    lms_off[c] = inc - M;
+    if (c == 255) lms_off[256] = total;
+}
+
+// LMS positions in text order: lmspos[lmsrank[w] + k] = position of the k-th
+// set bit of lmsb[w].  (reference P15, src/table.rs:512-520)
+__global__ void __launch_bounds__(BLK) k_lms_positions(const uint32_t *lmsb, const uint32_t *lmsrank, uint64_t nw,
+                                                       uint32_t *lmspos) {
+    uint64_t w = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+    if (w >= nw) return;
+    uint32_t bits = lmsb[w];
+    uint32_t r = lmsrank[w];
+    while (bits) {
+        uint32_t j = __ffs(bits) - 1;
+        bits &= bits - 1;
+        lmspos[r++] = (uint32_t)(w * 32 + j);
+    }
+}
+
+// rank of an LMS position among LMS positions in text order
+__device__ __forceinline__ uint32_t lms_text_rank(const uint32_t *__restrict__ lmsb,
+                                                  const uint32_t *__restrict__ lmsrank, uint32_t pos) {
+    uint32_t w = pos >> 5;
+    return __ldg(lmsrank + w) + __popc(__ldg(lmsb + w) & ((1u << (pos & 31)) - 1u));
+}
+__device__ __forceinline__ uint32_t bit_at(const uint32_t *__restrict__ bm, uint32_t pos) {
+    return (__ldg(bm + (pos >> 5)) >> (pos & 31)) & 1u;
+}
+
+}  // namespace b200sa

@@ -1,0 +1,255 @@
+// common.cuh -- block/warp primitives, generic scan / compaction / radix pass.
+// sm_100a only.  All kernels assume blockDim.x == BLK (256).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200sa {
+
+constexpr int BLK = 256;            // threads per block (== radix, one thread per digit)
+constexpr int NWARP = BLK / 32;
+constexpr int ITEMS = 8;            // items per thread in a ranking tile
+constexpr int TILE = BLK * ITEMS;   // 2048 items per tile
+constexpr uint32_t FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ---------------------------------------------------------------- scan ops
+struct OpSum {
+    __device__ __forceinline__ static uint32_t id() { return 0u; }
+    __device__ __forceinline__ static uint32_t op(uint32_t a, uint32_t b) { return a + b; }
+};
+struct OpMax {
+    __device__ __forceinline__ static uint32_t id() { return 0u; }
+    __device__ __forceinline__ static uint32_t op(uint32_t a, uint32_t b) { return a > b ? a : b; }
+};
+
+template <class Op>
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, v, o);
+        if ((int)lane_id() >= o) v = Op::op(v, t);
+    }
+    return v;
+}
+
+// Block-wide inclusive scan of one value per thread.  s_w: NWARP+1 words of
+// shared memory.  Returns the inclusive result; *total gets the block total.
+template <class Op>
+__device__ __forceinline__ uint32_t block_incl_scan(uint32_t v, uint32_t *s_w, uint32_t *total) {
+    uint32_t inc = warp_incl_scan<Op>(v);
+    __syncthreads();                       // protect s_w from a previous use
+    if (lane_id() == 31) s_w[warp_id()] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = Op::id();
+        for (int w = 0; w < NWARP; w++) {
+            uint32_t t = s_w[w];
+            s_w[w] = run;                  // exclusive prefix of warp w
+            run = Op::op(run, t);
+        }
+        s_w[NWARP] = run;
+    }
+    __syncthreads();
+    *total = s_w[NWARP];
+    return Op::op(s_w[warp_id()], inc);
+}
+
+// ------------------------------------------------------- generic device scan
+// Three-kernel reduce / scan-partials / apply over N elements given by an
+// input functor In(i) -> u32.  Out(i, exclusive, value) consumes the result.
+// Each block owns a contiguous chunk of SCAN_CHUNK elements.
+constexpr int SCAN_IPT = 16;
+constexpr int SCAN_CHUNK = BLK * SCAN_IPT;   // 4096
+
+template <class Op, class InF>
+__global__ void __launch_bounds__(BLK) k_scan_reduce(InF in, uint64_t n, uint32_t *partial) {
+    __shared__ uint32_t s_w[NWARP + 1];
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK;
+    uint32_t acc = Op::id();
+#pragma unroll 4
+    for (int k = 0; k < SCAN_IPT; k++) {
+        uint64_t i = base + (uint64_t)k * BLK + threadIdx.x;
+        if (i < n) acc = Op::op(acc, in(i));
+    }
+    uint32_t total;
+    block_incl_scan<Op>(acc, s_w, &total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+// Single block: in-place exclusive scan of partial[0..nb); total -> *out_total.
+template <class Op>
+__global__ void __launch_bounds__(BLK) k_scan_partials(uint32_t *partial, uint32_t nb, uint32_t *out_total) {
+    __shared__ uint32_t s_w[NWARP + 1];
+    uint32_t carry = Op::id();
+    for (uint32_t b0 = 0; b0 < nb; b0 += BLK) {
+        uint32_t i = b0 + threadIdx.x;
+        uint32_t v = i < nb ? partial[i] : Op::id();
+        uint32_t total;
+        uint32_t inc = block_incl_scan<Op>(v, s_w, &total);
+        // exclusive = carry op (inclusive without own value); recompute via shuffle-free trick
+        uint32_t prev = __shfl_up_sync(FULL, inc, 1);
+        uint32_t exc;
+        if (lane_id() == 0) exc = s_w[warp_id()];          // exclusive prefix of this warp
+        else exc = prev;
+        if (i < nb) partial[i] = Op::op(carry, exc);
+        carry = Op::op(carry, total);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && out_total) *out_total = carry;
+}
+
+// Warp-blocked layout: warp w owns SCAN_IPT*32 consecutive elements of the
+// chunk, read in SCAN_IPT coalesced rounds of 32; each round is one warp scan
+// with a running carry, then one cross-warp fix-up.
+template <class Op, class InF, class OutF>
+__global__ void __launch_bounds__(BLK) k_scan_apply(InF in, OutF out, uint64_t n, const uint32_t *partial_excl) {
+    __shared__ uint32_t s_w[NWARP + 1];
+    const uint32_t w = warp_id(), l = lane_id();
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)w * (SCAN_IPT * 32) + l;
+    uint32_t v[SCAN_IPT], exc[SCAN_IPT];
+    uint32_t carry = Op::id();
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        uint64_t i = base + (uint64_t)k * 32;
+        v[k] = (i < n) ? in(i) : Op::id();
+        uint32_t inc = warp_incl_scan<Op>(v[k]);
+        uint32_t prev = __shfl_up_sync(FULL, inc, 1);
+        exc[k] = Op::op(carry, l == 0 ? Op::id() : prev);
+        carry = Op::op(carry, __shfl_sync(FULL, inc, 31));
+    }
+    if (l == 0) s_w[w] = carry;           // warp total
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = partial_excl[blockIdx.x];
+        for (int ww = 0; ww < NWARP; ww++) {
+            uint32_t t = s_w[ww];
+            s_w[ww] = run;
+            run = Op::op(run, t);
+        }
+    }
+    __syncthreads();
+    uint32_t wbase = s_w[w];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        uint64_t i = base + (uint64_t)k * 32;
+        if (i < n) out(i, Op::op(wbase, exc[k]), v[k]);
+    }
+}
+
+// ------------------------------------------------------------- tile ranking
+// Stable multi-way ranking of one tile (TILE items, warp-blocked layout:
+// warp w, round r, lane l owns logical item  w*ITEMS*32 + r*32 + l).
+// dig[r] in [0,256) for valid items.  Requires s_wcnt[NWARP][256] zeroed and a
+// __syncthreads() before the call.  After the call (which ends with a
+// __syncthreads()):  position of item = digit_base[d] + s_wcnt[w][d] + rank[r]
+// and s_tcnt[d] = number of valid items with digit d in the tile.
+__device__ __forceinline__ void tile_rank(const uint32_t (&dig)[ITEMS], uint32_t validmask,
+                                          uint32_t (&rank)[ITEMS],
+                                          uint32_t (*s_wcnt)[256], uint32_t *s_tcnt) {
+    const uint32_t w = warp_id();
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        bool valid = (validmask >> r) & 1u;
+        uint32_t key = valid ? dig[r] : 0x100u;
+        uint32_t peers = __match_any_sync(FULL, key);
+        uint32_t below = __popc(peers & lt);
+        uint32_t base = valid ? s_wcnt[w][dig[r]] : 0u;
+        __syncwarp();
+        if (valid && below == 0) s_wcnt[w][dig[r]] = base + __popc(peers);
+        __syncwarp();
+        rank[r] = base + below;
+    }
+    __syncthreads();
+    {
+        uint32_t d = threadIdx.x;      // BLK == 256 digits
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < NWARP; ww++) {
+            uint32_t t = s_wcnt[ww][d];
+            s_wcnt[ww][d] = run;
+            run += t;
+        }
+        s_tcnt[d] = run;
+    }
+    __syncthreads();
+}
+
+// Warp-aggregated shared-memory histogram increment (all 32 lanes must call).
+__device__ __forceinline__ void hist_add(uint32_t *s_hist, uint32_t key, bool valid) {
+    uint32_t k = valid ? key : 0xffffffffu;
+    uint32_t peers = __match_any_sync(FULL, k);
+    if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
+}
+
+// ------------------------------------------------------------ radix passes
+// One stable LSD pass over N items whose 8-bit digit is DigF(i); MoveF(i,dst)
+// moves item i to output slot dst.  Block b owns tiles [b*tpb, (b+1)*tpb).
+// cnt layout: cnt[d*nb + b] (digit-major) so that one exclusive scan over the
+// whole array yields global bases.
+template <class DigF>
+__global__ void __launch_bounds__(BLK) k_radix_hist(DigF dig, uint64_t n, uint32_t tpb, uint32_t *cnt) {
+    __shared__ uint32_t s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t t0 = (uint64_t)blockIdx.x * tpb * TILE;
+    uint64_t t1 = t0 + (uint64_t)tpb * TILE;
+    if (t1 > n) t1 = n;
+    // round up so that every lane of every warp executes hist_add together
+    for (uint64_t i0 = t0; i0 < t1; i0 += BLK) {
+        uint64_t i = i0 + threadIdx.x;
+        bool valid = i < t1;
+        uint32_t d = valid ? dig(i) : 0u;
+        hist_add(s_hist, d, valid);
+    }
+    __syncthreads();
+    cnt[(uint64_t)threadIdx.x * gridDim.x + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+template <class DigF, class MoveF>
+__global__ void __launch_bounds__(BLK) k_radix_scatter(DigF dig, MoveF mv, uint64_t n, uint32_t tpb,
+                                                       const uint32_t *cnt_excl) {
+    __shared__ uint32_t s_wcnt[NWARP][256];
+    __shared__ uint32_t s_tcnt[256];
+    __shared__ uint32_t s_base[256];
+    s_base[threadIdx.x] = cnt_excl[(uint64_t)threadIdx.x * gridDim.x + blockIdx.x];
+    uint64_t t0 = (uint64_t)blockIdx.x * tpb * TILE;
+    uint64_t t1 = t0 + (uint64_t)tpb * TILE;
+    if (t1 > n) t1 = n;
+    const uint32_t w = warp_id(), l = lane_id();
+    for (uint64_t tb = t0; tb < t1; tb += TILE) {
+#pragma unroll
+        for (int ww = 0; ww < NWARP; ww++) s_wcnt[ww][threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t d[ITEMS], rank[ITEMS], vm = 0;
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            uint64_t i = tb + (uint64_t)w * (ITEMS * 32) + r * 32 + l;
+            bool valid = i < t1;
+            d[r] = valid ? dig(i) : 0u;
+            vm |= (valid ? 1u : 0u) << r;
+        }
+        tile_rank(d, vm, rank, s_wcnt, s_tcnt);
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+            if ((vm >> r) & 1u) {
+                uint64_t i = tb + (uint64_t)w * (ITEMS * 32) + r * 32 + l;
+                uint32_t dst = s_base[d[r]] + s_wcnt[w][d[r]] + rank[r];
+                mv(i, dst);
+            }
+        }
+        __syncthreads();
+        s_base[threadIdx.x] += s_tcnt[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+}  // namespace b200sa

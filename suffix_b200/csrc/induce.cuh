@@ -1,0 +1,252 @@
+// induce.cuh -- K4/K5: the L-then-S induced fill as ONE persistent cooperative
+// kernel per pass.  Replaces the four serial induce loops of the reference
+// (src/table.rs:421-448 and :543-573) together with Bins::head_insert /
+// tail_insert (src/table.rs:723-736).
+//
+// Parallel formulation (validated on CPU by tests/model_pipeline.py):
+//   * buckets are visited in scan order (ascending for L, descending for S);
+//   * inside bucket c the serial scan is a sequence of *lists*: the entries
+//     already present (induced from earlier buckets), then the entries those
+//     induce into c itself (chain round 1), then round 2, ... and finally the
+//     second list (L pass: the LMS suffixes of c; S pass: the L part of c);
+//   * every list is one stable multi-way partition step by d = T[s-1]:
+//     entry s emits s-1 into bucket d iff d is in the list's valid range
+//     (no type lookups are needed: the range encodes the type test).
+//   A step is either "big" (all blocks: count -> grid.sync -> scatter ->
+//   grid.sync) or "small" (<= TILE entries: block 0 alone, no grid sync; it
+//   keeps consuming small steps and then hands its state to the grid).
+// The per-bucket fill counters (the reference's bin pointers) live in shared
+// memory of every block and are advanced identically by all blocks.
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace b200sa {
+namespace cg = cooperative_groups;
+
+struct InduceArgs {
+    const uint8_t *text;     // level-0 text
+    uint32_t n;
+    uint32_t *sa;            // n slots
+    uint8_t *pred;           // n bytes: T[s-1] of the entry in SA slot p (big steps only)
+    const uint32_t *lms;     // LMS suffixes grouped by first byte (m)
+    uint8_t *lms_pred;       // m bytes
+    const uint32_t *bstart;  // [257]
+    const uint32_t *Lcnt;    // [256]
+    const uint32_t *Scnt;    // [256]
+    const uint32_t *lms_off; // [257]
+    uint32_t *blk_cnt;       // [2][gridDim.x][256]
+    uint32_t *g_fill;        // [256] hand-off after small episodes
+    int32_t *g_state;        // [4]   hand-off: c, phase, begin
+    uint32_t *err;           // [4]   err[0] != 0 => invariant violated
+};
+
+struct Seg {
+    const uint32_t *src;
+    uint8_t *pred;
+    uint32_t base;   // physical index of logical item 0
+    uint32_t len;
+    uint32_t lo, hi; // valid destination range (inclusive)
+    int rev;         // logical k -> physical base - k
+};
+
+struct IndShared {
+    uint32_t bstart[257];
+    uint32_t Lcnt[256];
+    uint32_t S_or_lmsoff[257];   // L pass: lms_off; S pass: Scnt
+    uint32_t fill[256];
+    uint32_t base[256];
+    uint32_t hist[256];
+    uint32_t tcnt[256];
+    uint32_t wcnt[NWARP][256];
+    // broadcast area
+    int32_t st_c, st_phase;
+    uint32_t st_begin;
+    int32_t ns_c, ns_phase;
+    uint32_t ns_begin;
+    int32_t has;
+    Seg seg;
+};
+
+enum { MODE_COUNT = 0, MODE_SCATTER = 1, MODE_SMALL = 2 };
+
+// Processes logical items [t0, t0+TILE) ∩ [0, g.len) of segment g.
+template <bool SPASS, int MODE>
+__device__ __forceinline__ void induce_tile(const InduceArgs &A, IndShared &sh, const Seg &g, uint32_t t0) {
+    const uint32_t w = warp_id(), l = lane_id();
+    uint32_t s[ITEMS], d[ITEMS], rank[ITEMS], vm = 0;
+    if (MODE != MODE_COUNT) {
+#pragma unroll
+        for (int ww = 0; ww < NWARP; ww++) sh.wcnt[ww][threadIdx.x] = 0;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        uint32_t k = t0 + w * (ITEMS * 32) + r * 32 + l;
+        bool in = k < g.len;
+        uint32_t p = g.rev ? g.base - k : g.base + k;
+        s[r] = in ? __ldcg(g.src + p) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        uint32_t k = t0 + w * (ITEMS * 32) + r * 32 + l;
+        bool in = k < g.len;
+        uint32_t p = g.rev ? g.base - k : g.base + k;
+        if (MODE == MODE_SCATTER) d[r] = in ? (uint32_t)__ldcg(g.pred + p) : 0u;
+        else d[r] = (s[r] > 0) ? (uint32_t)__ldg(A.text + (s[r] - 1)) : 0u;
+        bool valid = in && s[r] > 0 && d[r] >= g.lo && d[r] <= g.hi;
+        vm |= (valid ? 1u : 0u) << r;
+        if (MODE == MODE_COUNT) {
+            if (in) g.pred[p] = (uint8_t)d[r];
+            hist_add(sh.hist, d[r], valid);
+        }
+    }
+    if (MODE == MODE_COUNT) return;
+    tile_rank(d, vm, rank, sh.wcnt, sh.tcnt);
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        if ((vm >> r) & 1u) {
+            uint32_t pos = sh.base[d[r]] + sh.wcnt[w][d[r]] + rank[r];
+            uint32_t slot = SPASS ? (sh.bstart[d[r] + 1] - 1u - pos) : (sh.bstart[d[r]] + pos);
+            A.sa[slot] = s[r] - 1u;
+        }
+    }
+    __syncthreads();
+    sh.base[threadIdx.x] += sh.tcnt[threadIdx.x];
+    __syncthreads();
+}
+
+// Thread 0: derive the next non-empty segment from (state, fill) without
+// consuming it; ns_* is the state to adopt once it has been processed.
+template <bool SPASS>
+__device__ void induce_peek(const InduceArgs &A, IndShared &sh) {
+    int32_t c = sh.st_c, phase = sh.st_phase;
+    uint32_t begin = sh.st_begin;
+    sh.has = 0;
+    while (SPASS ? (c >= 0) : (c <= 255)) {
+        if (phase == 0) {
+            uint32_t end = sh.fill[c];
+            if (end > begin) {
+                sh.seg.src = A.sa; sh.seg.pred = A.pred; sh.seg.len = end - begin;
+                if (SPASS) { sh.seg.base = sh.bstart[c + 1] - 1u - begin; sh.seg.lo = 0; sh.seg.hi = (uint32_t)c; sh.seg.rev = 1; }
+                else       { sh.seg.base = sh.bstart[c] + begin; sh.seg.lo = (uint32_t)c; sh.seg.hi = 255; sh.seg.rev = 0; }
+                sh.ns_c = c; sh.ns_phase = 0; sh.ns_begin = end; sh.has = 1;
+                return;
+            }
+            // chain exhausted: the part must be complete (reference invariant)
+            uint32_t want = SPASS ? sh.S_or_lmsoff[c] : sh.Lcnt[c];
+            if (end != want && blockIdx.x == 0) { A.err[0] = 1; A.err[1] = (uint32_t)c; A.err[2] = end; A.err[3] = want; }
+            phase = 1;
+        }
+        if (SPASS) {
+            uint32_t L = sh.Lcnt[c];
+            int32_t cc = c;
+            c = c - 1; phase = 0; begin = 0;
+            if (L > 0 && cc > 0) {
+                sh.seg.src = A.sa; sh.seg.pred = A.pred; sh.seg.len = L;
+                sh.seg.base = sh.bstart[cc] + L - 1u; sh.seg.lo = 0; sh.seg.hi = (uint32_t)(cc - 1); sh.seg.rev = 1;
+                sh.ns_c = c; sh.ns_phase = 0; sh.ns_begin = 0; sh.has = 1;
+                return;
+            }
+        } else {
+            uint32_t a = sh.S_or_lmsoff[c], b = sh.S_or_lmsoff[c + 1];
+            int32_t cc = c;
+            c = c + 1; phase = 0; begin = 0;
+            if (b > a && cc < 255) {
+                sh.seg.src = A.lms; sh.seg.pred = A.lms_pred; sh.seg.len = b - a;
+                sh.seg.base = a; sh.seg.lo = (uint32_t)(cc + 1); sh.seg.hi = 255; sh.seg.rev = 0;
+                sh.ns_c = c; sh.ns_phase = 0; sh.ns_begin = 0; sh.has = 1;
+                return;
+            }
+        }
+    }
+    sh.st_c = c; sh.st_phase = 0; sh.st_begin = 0;   // done
+}
+
+template <bool SPASS>
+__global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
+    __shared__ IndShared sh;
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
+
+    // ---- init: tables, fill counters, seed (suffix n-1 is L: src/table.rs:422-425)
+    sh.bstart[tid] = A.bstart[tid];
+    if (tid == 0) sh.bstart[256] = A.bstart[256];
+    sh.Lcnt[tid] = A.Lcnt[tid];
+    if (SPASS) sh.S_or_lmsoff[tid] = A.Scnt[tid];
+    else { sh.S_or_lmsoff[tid] = A.lms_off[tid]; if (tid == 0) sh.S_or_lmsoff[256] = A.lms_off[256]; }
+    uint32_t lastc = A.text[A.n - 1];
+    sh.fill[tid] = (!SPASS && tid == lastc) ? 1u : 0u;
+    if (tid == 0) { sh.st_c = SPASS ? 255 : 0; sh.st_phase = 0; sh.st_begin = 0; }
+    __syncthreads();
+    if (!SPASS && bid == 0 && tid == 0) A.sa[sh.bstart[lastc]] = A.n - 1u;
+    uint32_t bigcount = 0;
+
+    while (true) {
+        if (tid == 0) induce_peek<SPASS>(A, sh);
+        __syncthreads();
+        if (!sh.has) break;
+        if (sh.seg.len <= (uint32_t)TILE) {
+            // ---------------- small episode: block 0 alone
+            if (bid == 0) {
+                while (sh.has && sh.seg.len <= (uint32_t)TILE) {
+                    Seg g = sh.seg;
+                    sh.base[tid] = sh.fill[tid];
+                    __syncthreads();
+                    induce_tile<SPASS, MODE_SMALL>(A, sh, g, 0);
+                    sh.fill[tid] = sh.base[tid];
+                    if (tid == 0) { sh.st_c = sh.ns_c; sh.st_phase = sh.ns_phase; sh.st_begin = sh.ns_begin; }
+                    __syncthreads();
+                    if (tid == 0) induce_peek<SPASS>(A, sh);
+                    __syncthreads();
+                }
+                A.g_fill[tid] = sh.fill[tid];
+                if (tid == 0) { A.g_state[0] = sh.st_c; A.g_state[1] = sh.st_phase; A.g_state[2] = (int32_t)sh.st_begin; }
+            }
+            grid.sync();
+            if (bid != 0) {
+                sh.fill[tid] = __ldcg(A.g_fill + tid);
+                if (tid == 0) {
+                    sh.st_c = __ldcg(A.g_state + 0); sh.st_phase = __ldcg(A.g_state + 1);
+                    sh.st_begin = (uint32_t)__ldcg(A.g_state + 2);
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        // -------------------- big step: all blocks
+        Seg g = sh.seg;
+        uint32_t *cntbuf = A.blk_cnt + (size_t)(bigcount & 1u) * G * 256u;
+        bigcount++;
+        uint32_t tiles = (g.len + TILE - 1) / TILE;
+        uint32_t tpb = (tiles + G - 1) / G;
+        uint32_t nact = (tiles + tpb - 1) / tpb;
+        uint32_t tb0 = bid * tpb, tb1 = tb0 + tpb;
+        if (tb1 > tiles) tb1 = tiles;
+        // phase A: count + remember predecessors
+        sh.hist[tid] = 0;
+        __syncthreads();
+        for (uint32_t t = tb0; t < tb1; t++) induce_tile<SPASS, MODE_COUNT>(A, sh, g, t * TILE);
+        __syncthreads();
+        if (bid < nact) cntbuf[(size_t)bid * 256u + tid] = sh.hist[tid];
+        grid.sync();
+        // phase B: offsets, scatter
+        {
+            uint32_t base = sh.fill[tid], tot = 0;
+            for (uint32_t b = 0; b < nact; b++) {
+                uint32_t v = __ldcg(cntbuf + (size_t)b * 256u + tid);
+                if (b < bid) base += v;
+                tot += v;
+            }
+            sh.base[tid] = base;
+            __syncthreads();
+            for (uint32_t t = tb0; t < tb1; t++) induce_tile<SPASS, MODE_SCATTER>(A, sh, g, t * TILE);
+            __syncthreads();
+            sh.fill[tid] += tot;
+        }
+        if (tid == 0) { sh.st_c = sh.ns_c; sh.st_phase = sh.ns_phase; sh.st_begin = sh.ns_begin; }
+        grid.sync();
+    }
+}
+
+}  // namespace b200sa

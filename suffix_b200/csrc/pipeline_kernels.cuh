@@ -1,0 +1,247 @@
+// pipeline_kernels.cuh -- functors and small kernels for the glue phases:
+//   K3  LMS grouping by first byte            (reference P5,  src/table.rs:411-416)
+//   K6  compaction of sorted LMS substrings   (reference P10, src/table.rs:450-463)
+//   K7  naming by neighbour equality          (reference P11, src/table.rs:465-482, wstring_equal :802-820)
+//   K8  reduced string in text order          (reference P12, src/table.rs:484-492)
+//   K9  base-case inversion                   (reference P13, src/table.rs:501-506)
+//   K10 un-rename ranks -> text positions     (reference P15-P16, src/table.rs:512-530)
+//   rank-pair doubling on the reduced string  (stands in for the recursion at src/table.rs:499)
+//   K12/K13 inverse SA + Kasai-style LCP      (reference semantics src/table.rs:348-361)
+//   batched positions()                       (reference src/table.rs:223-259)
+#pragma once
+#include "classify.cuh"
+
+namespace b200sa {
+
+// ------------------------------------------------------------ scan functors
+struct InPopcWords {            // popcount of bitmap words
+    const uint32_t *bm;
+    __device__ uint32_t operator()(uint64_t i) const { return __popc(bm[i]); }
+};
+struct OutStoreExcl {           // out[i] = exclusive prefix
+    uint32_t *out;
+    __device__ void operator()(uint64_t i, uint32_t exc, uint32_t) const { out[i] = exc; }
+};
+struct InArray {
+    const uint32_t *a;
+    __device__ uint32_t operator()(uint64_t i) const { return a[i]; }
+};
+
+// K6: keep SA entries that are LMS positions
+struct InIsLmsEntry {
+    const uint32_t *sa; const uint32_t *lmsb;
+    __device__ uint32_t operator()(uint64_t i) const { return bit_at(lmsb, sa[i]); }
+};
+struct OutCompactSa {
+    const uint32_t *sa; uint32_t *out;
+    __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const { if (v) out[exc] = sa[i]; }
+};
+
+// ------------------------------------------------------------ K3 functors
+struct DigTextAtPos {           // digit = first byte of the LMS suffix
+    const uint8_t *text; const uint32_t *pos;
+    __device__ uint32_t operator()(uint64_t i) const { return __ldg(text + pos[i]); }
+};
+struct MoveU32 {
+    const uint32_t *in; uint32_t *out;
+    __device__ void operator()(uint64_t i, uint32_t dst) const { out[dst] = in[i]; }
+};
+
+// ------------------------------------------------------------ K7 naming
+// LMS-substring equality with the reference's semantics (src/table.rs:802-820):
+// equal chars and equal type class position by position; equal once a later
+// position of either is a Valley; running off the text means different.
+__device__ __forceinline__ bool lms_substr_equal(const uint8_t *__restrict__ text, uint32_t n,
+                                                 const uint32_t *__restrict__ stype,
+                                                 const uint32_t *__restrict__ lmsb, uint32_t a, uint32_t b) {
+    uint32_t i = a, j = b;
+    while (i < n && j < n) {
+        if (__ldg(text + i) != __ldg(text + j)) return false;
+        if (bit_at(stype, i) != bit_at(stype, j)) return false;
+        if (i > a && (bit_at(lmsb, i) || bit_at(lmsb, j))) return true;
+        i++; j++;
+    }
+    return false;
+}
+// flag[i] = 1 iff sorted LMS substring i starts a new name
+__global__ void __launch_bounds__(BLK) k_name_flags(const uint8_t *__restrict__ text, uint32_t n,
+                                                    const uint32_t *__restrict__ stype,
+                                                    const uint32_t *__restrict__ lmsb,
+                                                    const uint32_t *__restrict__ sorted, uint32_t m, uint8_t *flag) {
+    uint32_t i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= m) return;
+    uint8_t f = 1;
+    if (i > 0) f = lms_substr_equal(text, n, stype, lmsb, sorted[i], sorted[i - 1]) ? 0 : 1;
+    flag[i] = f;
+}
+struct InFlagU8 {
+    const uint8_t *f;
+    __device__ uint32_t operator()(uint64_t i) const { return f[i]; }
+};
+// K8: reduced[text_rank(sorted[i])] = name(i) = inclusive(flag) - 1
+struct OutReduced {
+    const uint32_t *sorted; const uint32_t *lmsb; const uint32_t *lmsrank; uint32_t *reduced;
+    __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const {
+        reduced[lms_text_rank(lmsb, lmsrank, sorted[i])] = exc + v - 1u;
+    }
+};
+
+// K9: all names unique -> SA of the reduced string is the inverse permutation
+__global__ void __launch_bounds__(BLK) k_invert_perm(const uint32_t *reduced, uint32_t m, uint32_t *sa_r) {
+    uint32_t k = blockIdx.x * BLK + threadIdx.x;
+    if (k < m) sa_r[reduced[k]] = k;
+}
+// K10: sorted LMS suffixes = lmspos[sa_r[i]]
+__global__ void __launch_bounds__(BLK) k_unrename(const uint32_t *sa_r, const uint32_t *lmspos, uint32_t m,
+                                                  uint32_t *out) {
+    uint32_t i = blockIdx.x * BLK + threadIdx.x;
+    if (i < m) out[i] = lmspos[sa_r[i]];
+}
+
+// ------------------------------------------------------------ doubling
+__global__ void __launch_bounds__(BLK) k_iota(uint32_t *a, uint32_t m) {
+    uint32_t i = blockIdx.x * BLK + threadIdx.x;
+    if (i < m) a[i] = i;
+}
+template <class K>
+struct DigKey {
+    const K *keys; uint32_t shift;
+    __device__ uint32_t operator()(uint64_t i) const { return (uint32_t)(keys[i] >> shift) & 0xffu; }
+};
+template <class K>
+struct MoveKV {
+    const K *kin; const uint32_t *vin; K *kout; uint32_t *vout;
+    __device__ void operator()(uint64_t i, uint32_t dst) const { kout[dst] = kin[i]; vout[dst] = vin[i]; }
+};
+// group-start scan input: (key differs from predecessor) ? position id : 0
+// pos == nullptr -> the position id is the index itself.
+template <class K>
+struct InGroupStart {
+    const K *keys; const uint32_t *pos;
+    __device__ uint32_t operator()(uint64_t i) const {
+        bool head = (i == 0) || (keys[i] != keys[i - 1]);
+        return head ? (pos ? pos[i] : (uint32_t)i) : 0u;
+    }
+};
+// consumes the inclusive max-scan: grp[i] = start slot of i's group,
+// rank[suffix] = grp + 1, and (optionally) sa_r[slot] = suffix.
+struct OutGroupRank {
+    const uint32_t *suf; const uint32_t *pos; uint32_t *grp; uint32_t *rank; uint32_t *sa_r;
+    __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const {
+        uint32_t g = exc > v ? exc : v;
+        grp[i] = g;
+        uint32_t s = suf[i];
+        rank[s] = g + 1u;
+        if (sa_r) sa_r[pos ? pos[i] : (uint32_t)i] = s;
+    }
+};
+// active = member of a group with more than one element
+template <class K>
+struct InActive {
+    const K *keys; uint64_t cnt;
+    __device__ uint32_t operator()(uint64_t i) const {
+        bool head = (i == 0) || (keys[i] != keys[i - 1]);
+        bool tail = (i + 1 == cnt) || (keys[i + 1] != keys[i]);
+        return (head && tail) ? 0u : 1u;
+    }
+};
+struct OutCompactActive {
+    const uint32_t *pos; const uint32_t *suf; const uint32_t *grp;   // pos==nullptr -> index
+    uint32_t *opos; uint32_t *osuf; uint32_t *ogrp;
+    __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const {
+        if (v) { opos[exc] = pos ? pos[i] : (uint32_t)i; osuf[exc] = suf[i]; ogrp[exc] = grp[i]; }
+    }
+};
+// key = (group start << b2) | rank[suffix + h]   (0 beyond the end: a proper
+// prefix sorts first, matching slice `cmp`, src/table.rs:374)
+__global__ void __launch_bounds__(BLK) k_pair_keys(const uint32_t *agrp, const uint32_t *asuf, const uint32_t *rank,
+                                                   uint32_t na, uint32_t m, uint32_t h, uint32_t b2, uint64_t *keys) {
+    uint32_t k = blockIdx.x * BLK + threadIdx.x;
+    if (k >= na) return;
+    uint64_t s2 = (uint64_t)asuf[k] + h;
+    uint32_t r2 = s2 < m ? rank[s2] : 0u;
+    keys[k] = ((uint64_t)agrp[k] << b2) | r2;
+}
+
+// ------------------------------------------------------------ LCP
+__global__ void __launch_bounds__(BLK) k_isa(const uint32_t *sa, uint32_t n, uint32_t *isa) {
+    uint32_t i = blockIdx.x * BLK + threadIdx.x;
+    if (i < n) isa[sa[i]] = i;
+}
+// Kasai over chunks of LCP_CHUNK consecutive text positions per thread: the
+// first position of a chunk starts from h=0, the rest reuse h-1.
+constexpr int LCP_CHUNK = 32;
+__global__ void __launch_bounds__(BLK) k_lcp_kasai(const uint8_t *__restrict__ text, uint32_t n,
+                                                   const uint32_t *__restrict__ sa,
+                                                   const uint32_t *__restrict__ isa, uint32_t *lcp) {
+    uint64_t t = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+    uint64_t i0 = t * LCP_CHUNK;
+    if (i0 >= n) return;
+    uint64_t i1 = i0 + LCP_CHUNK;
+    if (i1 > n) i1 = n;
+    uint32_t h = 0;
+    for (uint64_t i = i0; i < i1; i++) {
+        uint32_t r = isa[i];
+        if (r == 0) { lcp[0] = 0; h = 0; continue; }
+        uint32_t j = __ldg(sa + r - 1);
+        uint64_t a = i + h, b = (uint64_t)j + h;
+        while (a < n && b < n && __ldg(text + a) == __ldg(text + b)) { a++; b++; }
+        h = (uint32_t)(a - i);
+        lcp[r] = h;
+        if (h > 0) h--;
+    }
+}
+
+// ------------------------------------------------------------ batched positions
+__device__ __forceinline__ int cmp_query_suffix(const uint8_t *__restrict__ text, uint32_t n, uint32_t s,
+                                                const uint8_t *__restrict__ q, uint32_t m, bool *is_prefix) {
+    // compares query with text[s..]; *is_prefix = suffix starts with query
+    uint32_t ls = n - s, l = ls < m ? ls : m, k = 0;
+    while (k < l) {
+        uint32_t a = q[k], b = __ldg(text + s + k);
+        if (a != b) { *is_prefix = false; return a < b ? -1 : 1; }
+        k++;
+    }
+    *is_prefix = (m <= ls);
+    return (m <= ls) ? (m == ls ? 0 : -1) : 1;
+}
+// One thread per query: reference early-outs (src/table.rs:228-235), then the
+// two binary searches (:244-250).
+__global__ void __launch_bounds__(BLK) k_positions(const uint8_t *__restrict__ text, uint32_t n,
+                                                   const uint32_t *__restrict__ sa, const uint8_t *__restrict__ qs,
+                                                   const uint64_t *__restrict__ qoff, uint32_t nq,
+                                                   uint32_t *out_start, uint32_t *out_end) {
+    uint32_t qi = blockIdx.x * BLK + threadIdx.x;
+    if (qi >= nq) return;
+    const uint8_t *q = qs + qoff[qi];
+    uint32_t m = (uint32_t)(qoff[qi + 1] - qoff[qi]);
+    uint32_t start = 0, end = 0;
+    if (n > 0 && m > 0) {
+        bool pre;
+        int c0 = cmp_query_suffix(text, n, sa[0], q, m, &pre);
+        bool out = (c0 < 0 && !pre);
+        if (!out) { bool p2; out = cmp_query_suffix(text, n, sa[n - 1], q, m, &p2) > 0; }
+        if (!out) {
+            uint32_t lo = 0, hi = n;
+            while (lo < hi) {                               // first suffix >= query
+                uint32_t mid = lo + (hi - lo) / 2;
+                bool p;
+                int c = cmp_query_suffix(text, n, sa[mid], q, m, &p);
+                if (c <= 0) hi = mid; else lo = mid + 1;
+            }
+            start = lo;
+            uint32_t lo2 = 0, hi2 = n - start;
+            while (lo2 < hi2) {                             // first suffix not starting with query
+                uint32_t mid = lo2 + (hi2 - lo2) / 2;
+                bool p;
+                cmp_query_suffix(text, n, sa[start + mid], q, m, &p);
+                if (!p) hi2 = mid; else lo2 = mid + 1;
+            }
+            end = start + lo2;
+        }
+    }
+    out_start[qi] = start;
+    out_end[qi] = end;
+}
+
+}  // namespace b200sa

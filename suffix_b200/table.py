@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's `SuffixTable` (src/table.rs:54-294).
+
+Construction (`SuffixTable(text)` == `SuffixTable::new`, src/table.rs:78-85)
+and `lcp_lens` (src/table.rs:130-138) call the CUDA library through the
+C-ABI; the bookkeeping and the O(m log n) queries stay on the host exactly
+like the reference (src/table.rs:197-293).
+"""
+import threading
+
+import numpy as np
+
+from . import _lib
+
+_lock = threading.Lock()
+
+
+def _as_bytes(text) -> bytes:
+    if isinstance(text, str):
+        return text.encode("utf-8")          # byte-level, like `Utf8` (src/table.rs:778-800)
+    if isinstance(text, (bytes, bytearray, memoryview)):
+        return bytes(text)
+    return np.ascontiguousarray(text, dtype=np.uint8).tobytes()
+
+
+class SuffixTable:
+    """A sequence of lexicographically sorted suffixes (u32 byte offsets)."""
+
+    def __init__(self, text, *, device: int = 0, _table=None):
+        """SuffixTable::new (src/table.rs:78-85): O(n) construction on the GPU.
+        Raises if the text exceeds 2^32-1 bytes (the reference panics, :380)."""
+        self._text = _as_bytes(text)
+        self._device = device
+        if _table is not None:
+            self._table = _table
+            return
+        if len(self._text) > 0xFFFFFFFF:
+            raise OverflowError("text longer than 2^32-1 bytes")
+        t = np.frombuffer(self._text, dtype=np.uint8)
+        with _lock:                           # default context is not thread-safe
+            ctx = _lib.default_context(device)
+            self._table = ctx.build(t)
+            self._stats = ctx.stats()
+
+    # src/table.rs:111-119
+    @classmethod
+    def from_parts(cls, text, table) -> "SuffixTable":
+        tb = _as_bytes(text)
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        assert len(tb) == len(table), "text and table lengths differ"   # assert_eq!, :117
+        return cls(tb, _table=table)
+
+    # src/table.rs:125-127
+    def into_parts(self):
+        return self._text, self._table
+
+    # src/table.rs:130-138 (semantics of lcp_lens_quadratic, :348-361)
+    def lcp_lens(self) -> np.ndarray:
+        t = np.frombuffer(self._text, dtype=np.uint8)
+        with _lock:
+            return _lib.default_context(self._device).lcp(t, self._table)
+
+    def table(self) -> np.ndarray:            # :142-144
+        return self._table
+
+    def text(self) -> bytes:                  # :148-150 (bytes; the reference returns &str)
+        return self._text
+
+    def __len__(self) -> int:                 # :156-158
+        return len(self._table)
+
+    def len(self) -> int:
+        return len(self._table)
+
+    def is_empty(self) -> bool:               # :162-164
+        return len(self._table) == 0
+
+    def suffix(self, i: int) -> str:          # :168-170
+        return self._text[int(self._table[i]):].decode("utf-8")
+
+    def suffix_bytes(self, i: int) -> bytes:  # :174-176
+        return self._text[int(self._table[i]):]
+
+    def __eq__(self, other):                  # derived PartialEq, :54
+        return isinstance(other, SuffixTable) and self._text == other._text and \
+            np.array_equal(self._table, other._table)
+
+    # ---- queries (host side, like the reference)
+    def contains(self, query) -> bool:        # :197-199
+        return self.any_position(query) is not None
+
+    def positions(self, query) -> np.ndarray:
+        """src/table.rs:223-259: sub-slice of the table (SA order, unsorted)."""
+        text, q = self._text, _as_bytes(query)
+        n, tab = len(text), self._table
+        empty = tab[0:0]
+        if n == 0 or len(q) == 0:
+            return empty
+        s0 = text[int(tab[0]):]
+        if (q < s0 and not s0.startswith(q)) or q > text[int(tab[n - 1]):]:
+            return empty
+        lo, hi = 0, n                         # binary_search, :900-914
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if q <= text[int(tab[mid]):]:
+                hi = mid
+            else:
+                lo = mid + 1
+        start = lo
+        lo, hi = 0, n - start
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if not text.startswith(q, int(tab[start + mid])):
+                hi = mid
+            else:
+                lo = mid + 1
+        end = start + lo
+        return empty if start > end else tab[start:end]
+
+    def any_position(self, query):
+        """src/table.rs:279-293: some position of `query`, or None."""
+        text, q = self._text, _as_bytes(query)
+        if len(q) == 0:
+            return None
+        tab = self._table
+        lo, hi = 0, len(tab)
+        m = len(q)
+        while lo < hi:
+            mid = (lo + hi) // 2
+            s = int(tab[mid])
+            head = text[s:s + m]
+            if head == q:
+                return s
+            if head < q:
+                lo = mid + 1
+            else:
+                hi = mid
+        return None
+
+    def last_stats(self) -> dict:
+        return getattr(self, "_stats", {})
+
+    def __repr__(self):
+        return "SuffixTable(n=%d)" % len(self._table)

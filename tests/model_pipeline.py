@@ -1,0 +1,216 @@
+"""Executable model (pure Python, small inputs) of the *device* pipeline's
+algorithm: bucket-sequential / round-parallel induced sorting at level 0 and
+rank-pair doubling on the reduced string.  It exists to validate the parallel
+formulation (step semantics, validity ranges, fill accounting) against the
+oracle on a CPU, and to produce expected intermediate arrays for the GPU
+kernel unit tests.  TEST INFRASTRUCTURE ONLY -- never imported by suffix_b200.
+"""
+
+
+def classify(T):
+    """S-type bit per position, LMS bit per position (reference semantics:
+    last char is L, src/table.rs:592-615)."""
+    n = len(T)
+    S = [0] * n
+    for i in range(n - 2, -1, -1):
+        if T[i] < T[i + 1]:
+            S[i] = 1
+        elif T[i] > T[i + 1]:
+            S[i] = 0
+        else:
+            S[i] = S[i + 1]
+    lms = [0] * n
+    for i in range(1, n):
+        lms[i] = 1 if (S[i] and not S[i - 1]) else 0
+    return S, lms
+
+
+def bucket_tables(T, S, sigma=256):
+    Lc = [0] * sigma
+    Sc = [0] * sigma
+    for c, s in zip(T, S):
+        if s:
+            Sc[c] += 1
+        else:
+            Lc[c] += 1
+    bstart = [0] * (sigma + 1)
+    for c in range(sigma):
+        bstart[c + 1] = bstart[c] + Lc[c] + Sc[c]
+    return Lc, Sc, bstart
+
+
+def _step(T, SA, src, logical, lo, hi, spass, bstart, fill):
+    """One partition step over a logical list of *physical slot indices*
+    `logical` into `src`: every entry s with s>0 and lo <= T[s-1] <= hi emits
+    s-1 into bucket d=T[s-1], stably.  L pass fills heads upward, S pass fills
+    tails downward.  Returns per-destination counts (fill is updated)."""
+    cnt = {}
+    for p in logical:
+        s = src[p]
+        if s == 0:
+            continue
+        d = T[s - 1]
+        if d < lo or d > hi:
+            continue
+        k = fill[d] + cnt.get(d, 0)
+        if spass:
+            SA[bstart[d + 1] - 1 - k] = s - 1
+        else:
+            SA[bstart[d] + k] = s - 1
+        cnt[d] = cnt.get(d, 0) + 1
+    for d, v in cnt.items():
+        fill[d] += v
+    return cnt
+
+
+def induce(T, SA, lms_list, lms_off, Lc, Sc, bstart, sigma=256, stats=None):
+    """L pass then S pass.  lms_list is grouped by first char with offsets
+    lms_off[c]; within a group the order is the caller's (text order in stage
+    1, sorted order in stage 2)."""
+    n = len(T)
+    # ---- L pass (reference P6-P7 / P19: head inserts, left-to-right) ----
+    fill = [0] * sigma
+    c_last = T[n - 1]
+    SA[bstart[c_last]] = n - 1            # seed: suffix n-1 is L by definition
+    fill[c_last] = 1
+    steps = 0
+    for c in range(sigma):
+        if bstart[c + 1] == bstart[c]:
+            continue
+        begin, end = 0, fill[c]
+        while end > begin:                # chain rounds inside bucket c
+            _step(T, SA, SA, range(bstart[c] + begin, bstart[c] + end), c, sigma - 1,
+                  False, bstart, fill)
+            steps += 1
+            begin, end = end, fill[c]
+        assert fill[c] == Lc[c], (c, fill[c], Lc[c])
+        if lms_off[c + 1] > lms_off[c] and c + 1 <= sigma - 1:
+            _step(T, SA, lms_list, range(lms_off[c], lms_off[c + 1]), c + 1, sigma - 1,
+                  False, bstart, fill)
+            steps += 1
+    # ---- S pass (reference P8-P9 / P20: tail inserts, right-to-left) ----
+    fill = [0] * sigma
+    for c in range(sigma - 1, -1, -1):
+        if bstart[c + 1] == bstart[c]:
+            continue
+        begin, end = 0, fill[c]
+        while end > begin:
+            top = bstart[c + 1] - 1
+            _step(T, SA, SA, range(top - begin, top - end, -1), 0, c, True, bstart, fill)
+            steps += 1
+            begin, end = end, fill[c]
+        assert fill[c] == Sc[c], (c, fill[c], Sc[c])
+        if Lc[c] > 0 and c > 0:
+            top = bstart[c] + Lc[c] - 1
+            _step(T, SA, SA, range(top, bstart[c] - 1, -1), 0, c - 1, True, bstart, fill)
+            steps += 1
+    if stats is not None:
+        stats["steps"] = stats.get("steps", 0) + steps
+
+
+def lms_equal(T, S, lms, a, b):
+    """LMS-substring equality, src/table.rs:802-820 semantics."""
+    n = len(T)
+    i, j = a, b
+    while i < n and j < n:
+        if T[i] != T[j] or S[i] != S[j]:
+            return False
+        if i > a and (lms[i] or lms[j]):
+            return True
+        i += 1
+        j += 1
+    return False
+
+
+def doubling_sa(R):
+    """Suffix array of the reduced string by rank-pair doubling with
+    group-start ranks; only non-singleton groups stay active."""
+    m = len(R)
+    sa = sorted(range(m), key=lambda i: R[i])              # stable radix sort by name
+    rank = [0] * m
+    grp = [0] * m
+    for p in range(m):
+        grp[p] = p if (p == 0 or R[sa[p]] != R[sa[p - 1]]) else grp[p - 1]
+        rank[sa[p]] = grp[p] + 1
+    def active_of(keys):
+        k = len(keys)
+        return [q for q in range(k)
+                if not ((q == 0 or keys[q] != keys[q - 1]) and (q == k - 1 or keys[q + 1] != keys[q]))]
+    act = active_of([grp[p] for p in range(m)])
+    apos = act[:]
+    asuf = [sa[p] for p in act]
+    agrp = [grp[p] for p in act]
+    h = 1
+    rounds = 0
+    while apos:
+        rounds += 1
+        keys = [(agrp[k], rank[asuf[k] + h] if asuf[k] + h < m else 0) for k in range(len(apos))]
+        order = sorted(range(len(apos)), key=lambda k: keys[k])
+        skeys = [keys[k] for k in order]
+        ssuf = [asuf[k] for k in order]
+        ngrp = [0] * len(apos)
+        for k in range(len(apos)):
+            sa[apos[k]] = ssuf[k]
+            ngrp[k] = apos[k] if (k == 0 or skeys[k] != skeys[k - 1]) else ngrp[k - 1]
+        for k in range(len(apos)):
+            rank[ssuf[k]] = ngrp[k] + 1
+        keep = active_of(skeys)
+        apos = [apos[k] for k in keep]
+        asuf = [ssuf[k] for k in keep]
+        agrp = [ngrp[k] for k in keep]
+        h *= 2
+    return sa, rounds
+
+
+def build_sa(T, sigma=256, stats=None):
+    """Whole pipeline; T is a list/bytes of ints < sigma."""
+    T = list(T)
+    n = len(T)
+    if n == 0:
+        return []
+    if n == 1:
+        return [0]
+    S, lms = classify(T)
+    Lc, Sc, bstart = bucket_tables(T, S, sigma)
+    lmspos = [i for i in range(n) if lms[i]]
+    m = len(lmspos)
+    lms_cnt = [0] * sigma
+    for p in lmspos:
+        lms_cnt[T[p]] += 1
+    lms_off = [0] * (sigma + 1)
+    for c in range(sigma):
+        lms_off[c + 1] = lms_off[c] + lms_cnt[c]
+    SA = [None] * n
+    if m > 0:
+        # stage 1: LMS grouped by first char (stable counting sort, text order)
+        grouped = sorted(lmspos, key=lambda p: T[p])
+        induce(T, SA, grouped, lms_off, Lc, Sc, bstart, sigma, stats)
+        assert sorted(SA) == list(range(n))
+        sorted_sub = [s for s in SA if lms[s]]
+        # naming
+        names = [0] * m
+        name = -1
+        for i, s in enumerate(sorted_sub):
+            if i == 0 or not lms_equal(T, S, lms, s, sorted_sub[i - 1]):
+                name += 1
+            names[i] = name
+        nnames = name + 1
+        text_rank = {p: k for k, p in enumerate(lmspos)}
+        R = [0] * m
+        for i, s in enumerate(sorted_sub):
+            R[text_rank[s]] = names[i]
+        if nnames == m:
+            sa_r = [0] * m
+            for k in range(m):
+                sa_r[R[k]] = k
+            rounds = 0
+        else:
+            sa_r, rounds = doubling_sa(R)
+        if stats is not None:
+            stats.update(m=m, names=nnames, rounds=rounds)
+        sorted_lms = [lmspos[k] for k in sa_r]
+    else:
+        sorted_lms = []
+    SA = [None] * n
+    induce(T, SA, sorted_lms, lms_off, Lc, Sc, bstart, sigma, stats)
+    return SA

@@ -1,0 +1,208 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle: bit-exact SA
+and LCP on the reference's KATs, the fixtures, adversarial families, random
+properties, and size-independent properties at larger sizes."""
+import hashlib
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle import oracle
+from suffix_b200 import SuffixTable, _lib, gen
+from tests import families
+
+pytestmark = pytest.mark.gpu
+KAT = families.kat()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _np(b):
+    return np.frombuffer(bytes(b), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("case", KAT["kat"], ids=lambda c: repr(c["text"])[:24])
+def test_kat(case):
+    # tests/tests.rs:22-70: naive(x) == sais(x) (text + table equality)
+    t = case["text"].encode("utf-8")
+    st_ = SuffixTable(case["text"])
+    assert st_.table().tolist() == case["sa"]
+    assert st_.text() == t and len(st_) == len(t)
+    assert st_.lcp_lens().tolist() == case["lcp"]
+    assert st_ == SuffixTable.from_parts(t, oracle.naive_sa(t))
+
+
+@pytest.mark.parametrize("case", KAT["positions"], ids=lambda c: repr((c["text"], c["query"]))[:40])
+def test_kat_positions(case):
+    # tests/tests.rs:100-213
+    st_ = SuffixTable(case["text"])
+    assert st_.positions(case["query"]).tolist() == case["positions"]
+    assert st_.contains(case["query"]) == bool(case["positions"])
+    hit = st_.any_position(case["query"])
+    assert (hit in case["positions"]) if case["positions"] else hit is None
+
+
+def test_parts_roundtrip():
+    # tests/tests.rs:171-179
+    sa = SuffixTable("poëzie")
+    data, table = sa.into_parts()
+    assert sa == SuffixTable.from_parts(data, table)
+
+
+@pytest.mark.parametrize("name", sorted(KAT["fixtures"]))
+def test_fixture_sha256(ctx, name):
+    info = KAT["fixtures"][name]
+    t = gen.fixture(name)
+    sa, lcp = ctx.build_lcp(t)
+    assert sa[:8].tolist() == info["sa_head"]
+    assert hashlib.sha256(sa.astype("<u4").tobytes()).hexdigest() == info["sa_sha256"]
+    assert hashlib.sha256(lcp.astype("<u4").tobytes()).hexdigest() == info["lcp_sha256"]
+
+
+@pytest.mark.parametrize("name,data", families.adversarial(), ids=lambda x: x if isinstance(x, str) else "")
+def test_adversarial(ctx, name, data):
+    t = _np(data)
+    want = oracle.sais(t)
+    sa, lcp = ctx.build_lcp(t)
+    assert np.array_equal(sa, want), name
+    assert np.array_equal(lcp, oracle.lcp_kasai(t, want)), name
+
+
+@pytest.mark.parametrize("maker,n", [("dna", 1_000_000), ("dna_nl", 1_000_001), ("bytes", 1_000_000),
+                                     ("english", 1_000_000), ("tiled", 1_000_000), ("dna", 5_000_000),
+                                     ("bytes", 5_000_000)])
+def test_medium_vs_oracle(ctx, maker, n):
+    if maker == "dna":
+        t = gen.dna(n)
+    elif maker == "dna_nl":
+        t = gen.dna(n, newline_tail=True)
+    elif maker == "bytes":
+        t = gen.rand_bytes(n)
+    elif maker == "english":
+        t = gen.english(n)
+    else:
+        t = gen.tiled(gen.fixture("AP009048_100000.fasta"), n)
+    want = oracle.sais(t)
+    sa = ctx.build(t)
+    assert np.array_equal(sa, want)
+    if maker != "tiled":     # tiled text has LCP ~ n: quadratic in any LCP algorithm that restarts
+        lcp = ctx.lcp(t, sa)
+        assert np.array_equal(lcp, oracle.lcp_kasai(t, want))
+
+
+def _check_sa_properties(t, sa, samples=200000, seed=1):
+    """Size-independent properties: permutation + sampled adjacent order."""
+    n = len(t)
+    assert len(sa) == n
+    seen = np.zeros(n, dtype=np.uint8)
+    seen[sa] = 1
+    assert int(seen.sum()) == n                       # permutation of 0..n-1
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(1, n, min(samples, n - 1))
+    tb = t.tobytes()
+    for i in idx.tolist():
+        a, b = int(sa[i - 1]), int(sa[i])
+        k = 64
+        while True:
+            x, y = tb[a:a + k], tb[b:b + k]
+            if x != y or a + k >= n or b + k >= n:
+                break
+            k *= 4
+        assert tb[a:a + k] < tb[b:b + k], (i, a, b)
+
+
+@pytest.mark.parametrize("maker,n", [("dna", 100_000_000), ("bytes", 100_000_000)])
+def test_full_size_properties(ctx, maker, n):
+    """BASELINE.json configs[1], configs[2] at full size: permutation +
+    sampled order + LCP spot checks (the oracle is too slow to run here in
+    seconds; bench.py compares a bounded sample against it)."""
+    t = gen.dna(n) if maker == "dna" else gen.rand_bytes(n)
+    sa = ctx.build(t)
+    _check_sa_properties(t, sa, samples=20000)
+    lcp = ctx.lcp(t, sa)
+    assert lcp[0] == 0
+    rng = np.random.default_rng(3)
+    tb = t.tobytes()
+    for i in rng.integers(1, n, 5000).tolist():
+        a, b, h = int(sa[i - 1]), int(sa[i]), int(lcp[i])
+        assert tb[a:a + h] == tb[b:b + h]
+        assert a + h == n or b + h == n or tb[a + h] != tb[b + h]
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.text(max_size=300))
+def test_prop_text(s):
+    # tests/tests.rs:73-96 prop_naive_equals_sais / prop_matches_naive, :215-221 prop_length
+    t = s.encode("utf-8")
+    tab = SuffixTable(s)
+    assert len(tab) == len(t)
+    assert np.array_equal(tab.table(), oracle.naive_sa(t))
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.binary(max_size=600))
+def test_prop_binary(b):
+    tab = SuffixTable(b)
+    assert np.array_equal(tab.table(), oracle.naive_sa(b))
+    if len(b):
+        assert np.array_equal(tab.lcp_lens(), oracle.lcp_quadratic(b, tab.table()))
+
+
+@settings(max_examples=100, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.text(max_size=100), st.integers(0, 255))
+def test_prop_positions(s, c):
+    # tests/tests.rs:223-243 prop_contains / prop_positions
+    q = chr(c)
+    tab = SuffixTable(s)
+    want = [i for i in range(len(s.encode())) if s.encode().startswith(q.encode(), i)]
+    assert sorted(tab.positions(q).tolist()) == want
+    assert tab.contains(q) == (q in s)
+
+
+def test_positions_dev_batch(ctx):
+    import torch
+    t = gen.fixture("AP009048_100000.fasta")
+    tab = SuffixTable(t.tobytes())
+    queries = [b"ACGT", b"GATTACA", b"T", b"\n", b"ZZZ", b"A" * 30, t.tobytes()[500:540], b"ACGTACGTAC"]
+    flat = np.frombuffer(b"".join(queries), dtype=np.uint8)
+    off = np.cumsum([0] + [len(q) for q in queries]).astype(np.uint64)
+    dev = torch.device("cuda:0")
+    d_t = torch.from_numpy(t.copy()).to(dev)
+    d_sa = torch.from_numpy(tab.table().astype(np.int64)).to(dev).to(torch.int32)  # same 4-byte payload
+    d_q = torch.from_numpy(flat.copy()).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_s = torch.zeros(len(queries), dtype=torch.int32, device=dev)
+    d_e = torch.zeros(len(queries), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.positions_dev(d_t.data_ptr(), len(t), d_sa.data_ptr(), d_q.data_ptr(), d_off.data_ptr(), len(queries),
+                      d_s.data_ptr(), d_e.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    s, e = d_s.cpu().numpy(), d_e.cpu().numpy()
+    for k, q in enumerate(queries):
+        assert tab.table()[s[k]:e[k]].tolist() == tab.positions(q).tolist(), q
+
+
+def test_build_dev_matches_host(ctx):
+    import torch
+    t = gen.dna(300_000)
+    dev = torch.device("cuda:0")
+    d_t = torch.from_numpy(t.copy()).to(dev)
+    d_sa = torch.empty(len(t), dtype=torch.int32, device=dev)
+    d_lcp = torch.empty(len(t), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.build_dev(d_t.data_ptr(), len(t), d_sa.data_ptr(), stream)
+    ctx.lcp_dev(d_t.data_ptr(), len(t), d_sa.data_ptr(), d_lcp.data_ptr(), stream)
+    torch.cuda.synchronize()
+    want = oracle.sais(t)
+    assert np.array_equal(d_sa.cpu().numpy().view(np.uint32), want)
+    assert np.array_equal(d_lcp.cpu().numpy().view(np.uint32), oracle.lcp_kasai(t, want))
+    # unaligned device pointer (exercises the internal aligned copy)
+    d_t2 = torch.from_numpy(np.concatenate([[0], t]).astype(np.uint8)).to(dev)[1:]
+    ctx.build_dev(d_t2.data_ptr(), len(t), d_sa.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sa.cpu().numpy().view(np.uint32), want)

@@ -1,0 +1,35 @@
+"""The parallel formulation used on the device (tests/model_pipeline.py) must
+produce the reference's suffix array on every family."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import oracle
+from tests import families, model_pipeline as mp
+
+KAT = families.kat()
+
+
+@pytest.mark.parametrize("case", KAT["kat"], ids=lambda c: repr(c["text"])[:24])
+def test_model_kat(case):
+    t = case["text"].encode("utf-8")
+    assert mp.build_sa(t) == case["sa"]
+
+
+@pytest.mark.parametrize("name,data", families.adversarial(), ids=lambda x: x if isinstance(x, str) else "")
+def test_model_adversarial(name, data):
+    data = data[:6000]
+    assert mp.build_sa(data) == oracle.sais(data).tolist()
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.binary(max_size=120))
+def test_model_prop_binary(t):
+    assert mp.build_sa(t) == oracle.naive_sa(t).tolist()
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.text(alphabet="abc", max_size=80))
+def test_model_prop_small_alphabet(s):
+    t = s.encode()
+    assert mp.build_sa(t) == oracle.naive_sa(t).tolist()
