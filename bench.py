@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric : MB/s of input text indexed (SuffixTable::new + lcp_lens, i.e. SA + LCP
+         build); MB = 1e6 bytes.
+N = 1  : configs[1] -- 100 MB synthetic DNA (sigma=4), generator G_dna of
+         SURVEY.md Appendix C; one "step" = one full SA + LCP build.
+N > 1  : the induce recursion is single-device by north_star, so ranks index
+         independent 100 MB texts (replicas, no data-path collective):
+         "scaling": "weak".
+
+value  : device-resident (text already in HBM, SA/LCP left in HBM), CUDA events
+         on the launching stream, max over ranks.
+e2e    : the same step through the host-buffer C-ABI (b200sa_build_lcp) with
+         pinned HOST buffers: H2D of the text and D2H of SA+LCP inside the
+         timed region.
+roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
+
+--impl reference: the reference's own CPU algorithm.  The reference is Rust and
+cannot be compiled in this image, so this arm times the oracle port
+(oracle/sais_oracle.c: restated sais() + lcp_lens()) on one host core (the
+reference is single-threaded), each step on a bounded prefix of the workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from suffix_b200 import gen  # noqa: E402
+
+N_TEXT = 100_000_000
+METRIC = "MB/s input text indexed (SA+LCP build)"
+UNIT = "MB/s"
+WORKLOAD = "100 MB synthetic DNA (sigma=4) SA-IS build + LCP, G_dna seed 0x5AFE5EED0000D7A4"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def _oracle_time(text_np, with_lcp=True):
+    from oracle import oracle          # CPU baseline leg: the one place bench.py executes oracle/
+    t0 = time.perf_counter()
+    sa = oracle.sais(text_np)
+    if with_lcp:
+        oracle.lcp_lens(text_np, sa)
+    return time.perf_counter() - t0, sa
+
+
+def run_reference(args):
+    rank, world, _ = _dist_env()
+    if rank != 0:
+        return 0
+    steps, warm = args.steps, args.warmup
+    # bound the whole run to ~150 s of CPU at ~4 MB/s
+    per_step = 150.0 / max(1, steps + warm)
+    n_ref = int(min(32_000_000, max(1_000_000, per_step * 4.0e6)))
+    text = gen.dna(n_ref)
+    for _ in range(warm):
+        _oracle_time(text)
+    ts = []
+    for _ in range(steps):
+        dt, _sa = _oracle_time(text)
+        ts.append(dt)
+    total = sum(ts)
+    val = n_ref * steps / 1e6 / total
+    sample = "first %d bytes of the workload per step (oracle port of sais()+lcp_lens(), 1 thread)" % n_ref
+    out = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": round(total / steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_bytes": N_TEXT, "sample_bytes_per_step": n_ref},
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from suffix_b200 import _lib
+
+    rank, world, local = _dist_env()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n = args.n
+    steps, warm = args.steps, args.warmup
+
+    # independent text per rank (replicas): seed + rank
+    text = gen.dna(n, seed=gen.SEED_DNA + rank)
+    ctx = _lib.Context(local)
+    ctx.set_timing(True)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    d_text = torch.from_numpy(text).to(dev)
+    d_sa = torch.empty(n, dtype=torch.int32, device=dev)
+    d_lcp = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        ctx.build_dev(d_text.data_ptr(), n, d_sa.data_ptr(), sptr)
+        ph = ctx.phase_times()
+        launches = ctx.stats()["kernel_launches"]
+        ctx.lcp_dev(d_text.data_ptr(), n, d_sa.data_ptr(), d_lcp.data_ptr(), sptr)
+        ph2 = ctx.phase_times()
+        launches += ctx.stats()["kernel_launches"]
+        return ph, ph2, launches
+
+    # ---------------- device-resident timing (`value`)
+    for _ in range(warm):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase_acc, launches = {}, 0
+    ev0.record(stream)
+    for _ in range(steps):
+        ph, ph2, l = step_dev()
+        launches += l
+        for k, v in ph + ph2:
+            phase_acc.setdefault(k, []).append(v)
+    ev1.record(stream)
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    stats = ctx.stats()
+    # SA-only share from the library's own phase events (same timed region)
+    sa_ms = sum(sum(v) for k, v in phase_acc.items() if not k.startswith("lcp")) / steps
+
+    # ---------------- end-to-end through the host-buffer C-ABI (`e2e`)
+    h_text = torch.from_numpy(text).pin_memory()
+    h_sa = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_lcp = torch.empty(n, dtype=torch.int32).pin_memory()
+    L = _lib.lib()
+
+    def step_host():
+        rc = L.b200sa_build_lcp(ctx._h, h_text.data_ptr(), n, h_sa.data_ptr(), h_lcp.data_ptr())
+        if rc != 0:
+            raise RuntimeError(L.b200sa_last_error(ctx._h).decode())
+
+    for _ in range(min(warm, 3)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_host()                       # synchronous: returns with SA/LCP in host memory
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    e2e_result_check = int(h_lcp[0].item()) + int(h_sa[0].item() >= 0)   # touch the result
+
+    # ---------------- max over ranks
+    if world > 1:
+        tt = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(tt[0].item()), float(tt[1].item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        total_bytes = n * world
+        value = total_bytes * steps / 1e6 / (ms_dev / 1e3)
+        e2e = total_bytes * steps / 1e6 / (ms_e2e / 1e3)
+        # ---- roofline of the dominant kernel: k_induce (persistent, 4 launches per build)
+        m = stats["m"]
+        nL = n / 2.0
+        # SURVEY.md Appendix D, level 0 (w = 1 byte): L pass 4n+(w+1)(m+nL)+4nL, S pass 4n+(w+1)n+4nS
+        bytes_L = 4 * n + 2 * (m + nL) + 4 * nL
+        bytes_S = 4 * n + 2 * n + 4 * (n - nL)
+        ind = {k: statistics.mean(v) for k, v in phase_acc.items() if k.startswith("induce")}
+        ind_ms = statistics.mean(ind.values()) if ind else None
+        alg = (bytes_L + bytes_S) / 2.0
+        achieved = alg / 1e9 / (ind_ms / 1e3) if ind_ms else None
+        traffic = None
+        ncu_p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        if os.path.exists(ncu_p):
+            try:
+                traffic = json.load(open(ncu_p)).get("k_induce", {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        phase_ms = {k: round(statistics.mean(v), 3) for k, v in phase_acc.items()}
+        dom_share = (sum(ind.values()) / (ms_dev / steps)) if ind else None
+        roof = {"bound": "hbm", "kernel": "k_induce<L|S> (mean of the 4 persistent launches per build)",
+                "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg),
+                "kernel_ms_per_launch": round(ind_ms, 4) if ind_ms else None,
+                "share_of_step": round(dom_share, 3) if dom_share else None,
+                "pipeline_bytes_per_input_byte_compulsory": 14}
+        # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            n_cpu = min(n, 32_000_000)
+            dt, sa_cpu = _oracle_time(text[:n_cpu])
+            cpu = {"value": round(n_cpu / 1e6 / dt, 3), "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "first %d bytes of the workload, oracle port of sais()+lcp_lens(), 1 thread of %d host cores"
+                             % (n_cpu, os.cpu_count() or 0), "seconds": round(dt, 2)}
+            # parity spot check on the same sample: GPU SA of the prefix == oracle SA
+            sa_gpu = ctx.build(np.ascontiguousarray(text[:n_cpu]))
+            cpu["gpu_matches_oracle_on_sample"] = bool(np.array_equal(sa_gpu, sa_cpu))
+        out = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": round(ms_dev / steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if n == N_TEXT else "%d-byte G_dna text" % n, "n_bytes_per_gpu": n,
+                       "parallelism": "replicas x%d (independent texts, no collective)" % world,
+                       "l2": "inputs larger than L2 (text 100 MB + SA 400 MB + LCP 400 MB per step)",
+                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8 * n,
+                    "ms_per_step": round(ms_e2e / steps, 3), "api": "b200sa_build_lcp (pinned host buffers)",
+                    "result_touch": e2e_result_check},
+            "gpu_launches": launches,
+            "sa_only": {"value": round(n * world / 1e6 / (sa_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(sa_ms, 3)},
+            "phase_ms": phase_ms,
+            "levels": {"n": n, "m": stats["m"], "names": stats["names"], "doubling_rounds": stats["doubling_rounds"]},
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_TEXT, help="text bytes per GPU (default: the 100 MB config)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -33,6 +33,8 @@ struct b200sa_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;   // stream of the current call
+    cudaStream_t copy_stream = nullptr;   // D2H of the SA overlapped with the LCP kernels
+    cudaEvent_t ev_sa = nullptr;
     int sm_count = 0;
     int induce_blocks = 0;
     std::string last_error;
@@ -156,6 +158,18 @@ static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, uint32_t *d_tot
     return B200SA_OK;
 }
 
+template <class Op, class InF>
+static int dev_reduce(b200sa_ctx *c, InF in, uint64_t n, uint32_t *d_total) {
+    if (n == 0) { CU_TRY(c, cudaMemsetAsync(d_total, 0, 4, c->stream)); return B200SA_OK; }
+    uint32_t nb = cdiv(n, SCAN_CHUNK);
+    TRY(ensure(c, c->scan_partial, (size_t)nb * 4));
+    uint32_t *part = ptr<uint32_t>(c->scan_partial);
+    LAUNCH(c, (k_scan_reduce<Op, InF>), nb, in, n, part);
+    LAUNCH(c, (k_scan_partials<Op>), 1, part, nb, d_total);
+    CU_TRY(c, cudaGetLastError());
+    return B200SA_OK;
+}
+
 constexpr uint32_t MAX_RADIX_BLOCKS = 1184;   // 148 SMs x 8
 
 template <class DigF, class MoveF>
@@ -196,6 +210,45 @@ static int bit_length(uint64_t x) {
 }
 
 // ------------------------------------------------------- reduced problem
+// Refinement rounds shared by both entry paths.  On entry the na active
+// suffixes (members of non-singleton groups) are listed in asuf with their SA
+// slots in c->p0 and group starts in c->g0; rank[] and sa_r hold the order by
+// the first h symbols.
+static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asuf, uint32_t *ascratch, uint64_t h,
+                           uint32_t *rounds_io) {
+    uint32_t *sa_r = ptr<uint32_t>(c->sa_r), *rank = ptr<uint32_t>(c->rank);
+    uint32_t *apos = ptr<uint32_t>(c->p0), *apos_next = ptr<uint32_t>(c->p1);
+    uint32_t *G0 = ptr<uint32_t>(c->g0), *G1 = ptr<uint32_t>(c->g1), *agrp = G0;
+    uint32_t *d_na = ptr<uint32_t>(c->small);
+    uint32_t rounds = *rounds_io;
+    if (na > 0) {
+        TRY(ensure(c, c->k64a, (size_t)na * 8));
+        TRY(ensure(c, c->k64b, (size_t)na * 8));
+    }
+    int b2 = bit_length(m);
+    while (na > 0) {
+        rounds++;
+        if (rounds > 40) { c->last_error = "doubling did not converge"; return B200SA_ERR_INTERNAL; }
+        uint64_t *KA = ptr<uint64_t>(c->k64a), *KB = ptr<uint64_t>(c->k64b), *K2;
+        uint32_t hh = h > 0xffffffffull ? 0xffffffffu : (uint32_t)h;
+        LAUNCH(c, k_pair_keys, cdiv(na, BLK), agrp, asuf, rank, na, m, hh, (uint32_t)b2, KA);
+        uint32_t *Vsorted;
+        TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, 2 * b2, &K2, &Vsorted));
+        uint32_t *Vother = (Vsorted == asuf) ? ascratch : asuf;
+        TRY((dev_scan<OpMax>(c, InGroupStart<uint64_t>{K2, apos}, OutGroupRank{Vsorted, apos, G1, rank, sa_r}, na, nullptr)));
+        TRY((dev_scan<OpSum>(c, InActive<uint64_t>{K2, na}, OutCompactActive{apos, Vsorted, G1, apos_next, Vother, G0}, na, d_na)));
+        TRY(read_words(c, d_na, 1));
+        na = c->h_pin[0];
+        asuf = Vother; ascratch = Vsorted;
+        uint32_t *t = apos; apos = apos_next; apos_next = t;
+        agrp = G0;
+        h *= 2;
+    }
+    *rounds_io = rounds;
+    return B200SA_OK;
+}
+
+
 // SA of the u32 string R[0..m) (all symbols < names) -> ctx->sa_r.
 // Stands in for the reference's recursion (src/table.rs:494-500): sort by
 // name, then refine (group, rank[i+h]) pairs, doubling h, keeping only
@@ -218,42 +271,43 @@ static int reduced_sa(b200sa_ctx *c, uint32_t *R, uint32_t m, uint32_t names, ui
     uint32_t *d_na = ptr<uint32_t>(c->small);
     uint32_t rounds = 0;
 
-    // round 0: sort suffixes by first symbol
+    // round 0: sort suffixes by their first k symbols (k chosen so that the
+    // key has about bit_length(m)+2 bits: random-like inputs become almost all
+    // singletons after one sort; k = 1 when the alphabet is already ~m).
     LAUNCH(c, k_iota, cdiv(m, BLK), V0, m);
-    uint32_t *Ks, *Vs;
-    int bits0 = bit_length(names > 0 ? names - 1 : 0);
-    if (bits0 < 1) bits0 = 1;
-    TRY(sort_pairs<uint32_t>(c, R, V0, ptr<uint32_t>(c->k32b), V1, m, bits0, &Ks, &Vs));
-    TRY((dev_scan<OpMax>(c, InGroupStart<uint32_t>{Ks, nullptr}, OutGroupRank{Vs, nullptr, G1, rank, sa_r}, m, nullptr)));
+    int bm = bit_length(m);
+    int bw = bit_length(names);               // symbols are stored +1 (0 = past the end)
+    if (bw < 1) bw = 1;
+    uint32_t k0 = 1;
+    if (bw + 3 < bm) {
+        k0 = (uint32_t)((bm + 2 + bw - 1) / bw);
+        if ((int)k0 * bw > 64) k0 = 64 / bw;
+    }
+    if (const char *e = getenv("B200SA_K0")) { int v = atoi(e); if (v >= 1 && v * bw <= 64) k0 = (uint32_t)v; }
+    uint32_t *Vs;
+    uint32_t na = 0;
+    if ((int)k0 * bw <= 32) {
+        uint32_t *KA = ptr<uint32_t>(c->k32b), *Ks;
+        LAUNCH(c, (k_multi_key<uint32_t>), cdiv(m, BLK), R, m, k0, (uint32_t)bw, KA);
+        // R itself is the ping-pong partner (it is dead once the keys exist)
+        TRY(sort_pairs<uint32_t>(c, KA, V0, R, V1, m, (int)k0 * bw, &Ks, &Vs));
+        TRY((dev_scan<OpMax>(c, InGroupStart<uint32_t>{Ks, nullptr}, OutGroupRank{Vs, nullptr, G1, rank, sa_r}, m, nullptr)));
+        uint32_t *Vf = (Vs == V0) ? V1 : V0;
+        TRY((dev_scan<OpSum>(c, InActive<uint32_t>{Ks, m}, OutCompactActive{nullptr, Vs, G1, P0, Vf, G0}, m, d_na)));
+    } else {
+        TRY(ensure(c, c->k64a, (size_t)m * 8));
+        TRY(ensure(c, c->k64b, (size_t)m * 8));
+        uint64_t *KA = ptr<uint64_t>(c->k64a), *KB = ptr<uint64_t>(c->k64b), *Ks;
+        LAUNCH(c, (k_multi_key<uint64_t>), cdiv(m, BLK), R, m, k0, (uint32_t)bw, KA);
+        TRY(sort_pairs<uint64_t>(c, KA, V0, KB, V1, m, (int)k0 * bw, &Ks, &Vs));
+        TRY((dev_scan<OpMax>(c, InGroupStart<uint64_t>{Ks, nullptr}, OutGroupRank{Vs, nullptr, G1, rank, sa_r}, m, nullptr)));
+        uint32_t *Vf = (Vs == V0) ? V1 : V0;
+        TRY((dev_scan<OpSum>(c, InActive<uint64_t>{Ks, m}, OutCompactActive{nullptr, Vs, G1, P0, Vf, G0}, m, d_na)));
+    }
     uint32_t *Vfree = (Vs == V0) ? V1 : V0;
-    TRY((dev_scan<OpSum>(c, InActive<uint32_t>{Ks, m}, OutCompactActive{nullptr, Vs, G1, P0, Vfree, G0}, m, d_na)));
     TRY(read_words(c, d_na, 1));
-    uint32_t na = c->h_pin[0];
-    uint32_t *asuf = Vfree, *ascratch = Vs, *apos = P0, *apos_next = P1, *agrp = G0;
-    if (na > 0) {
-        TRY(ensure(c, c->k64a, (size_t)na * 8));
-        TRY(ensure(c, c->k64b, (size_t)na * 8));
-    }
-    int b2 = bit_length(m);
-    uint64_t h = 1;
-    while (na > 0) {
-        rounds++;
-        if (rounds > 40) { c->last_error = "doubling did not converge"; return B200SA_ERR_INTERNAL; }
-        uint64_t *KA = ptr<uint64_t>(c->k64a), *KB = ptr<uint64_t>(c->k64b), *K2;
-        uint32_t hh = h > 0xffffffffull ? 0xffffffffu : (uint32_t)h;
-        LAUNCH(c, k_pair_keys, cdiv(na, BLK), agrp, asuf, rank, na, m, hh, (uint32_t)b2, KA);
-        uint32_t *Vsorted;
-        TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, 2 * b2, &K2, &Vsorted));
-        uint32_t *Vother = (Vsorted == asuf) ? ascratch : asuf;
-        TRY((dev_scan<OpMax>(c, InGroupStart<uint64_t>{K2, apos}, OutGroupRank{Vsorted, apos, G1, rank, sa_r}, na, nullptr)));
-        TRY((dev_scan<OpSum>(c, InActive<uint64_t>{K2, na}, OutCompactActive{apos, Vsorted, G1, apos_next, Vother, G0}, na, d_na)));
-        TRY(read_words(c, d_na, 1));
-        na = c->h_pin[0];
-        asuf = Vother; ascratch = Vsorted;
-        uint32_t *t = apos; apos = apos_next; apos_next = t;
-        agrp = G0;
-        h *= 2;
-    }
+    na = c->h_pin[0];
+    TRY(doubling_rounds(c, m, na, Vfree, Vs, k0, &rounds));
     if (rounds_out) *rounds_out = rounds;
     return B200SA_OK;
 }
@@ -355,9 +409,7 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
         TRY(mark(c, "name"));
         LAUNCH(c, k_name_flags, cdiv(m, BLK), text, n32, ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb),
                ptr<uint32_t>(c->sorted), m, ptr<uint8_t>(c->flag));
-        TRY((dev_scan<OpSum>(c, InFlagU8{ptr<uint8_t>(c->flag)},
-                             OutReduced{ptr<uint32_t>(c->sorted), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank), ptr<uint32_t>(c->reduced)},
-                             m, sm + 2)));
+        TRY((dev_reduce<OpSum>(c, InFlagU8{ptr<uint8_t>(c->flag)}, m, sm + 2)));
         TRY(read_words(c, sm + 1, 2));
         uint32_t cnt_lms = c->h_pin[0], names = c->h_pin[1];
         if (cnt_lms != m) {
@@ -365,13 +417,30 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
             c->last_error = b; return B200SA_ERR_INTERNAL;
         }
         c->stats.names = names;
+        // K8/K9 + recursion stand-in: the sorted LMS substrings already give the
+        // reduced suffixes ordered by their first symbol, so doubling starts at
+        // h = 1 without sorting the names again.
         TRY(mark(c, "reduced_sa"));
         TRY(ensure(c, c->sa_r, (size_t)m * 4));
-        if (names == m) {
-            LAUNCH(c, k_invert_perm, cdiv(m, BLK), ptr<uint32_t>(c->reduced), m, ptr<uint32_t>(c->sa_r));
-        } else {
-            uint32_t rounds = 0;
-            TRY(reduced_sa(c, ptr<uint32_t>(c->reduced), m, names, &rounds));
+        TRY(ensure(c, c->rank, (size_t)m * 4));
+        TRY(ensure(c, c->g1, (size_t)m * 4));
+        TRY((dev_scan<OpMax>(c, InFlagPos{ptr<uint8_t>(c->flag)},
+                             OutInitFromSorted{ptr<uint32_t>(c->sorted), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank),
+                                               ptr<uint32_t>(c->sa_r), ptr<uint32_t>(c->g1), ptr<uint32_t>(c->rank)},
+                             m, nullptr)));
+        if (names < m) {
+            TRY(ensure(c, c->v0, (size_t)m * 4));
+            TRY(ensure(c, c->v1, (size_t)m * 4));
+            TRY(ensure(c, c->p0, (size_t)m * 4));
+            TRY(ensure(c, c->p1, (size_t)m * 4));
+            TRY(ensure(c, c->g0, (size_t)m * 4));
+            TRY((dev_scan<OpSum>(c, InActive<uint32_t>{ptr<uint32_t>(c->g1), m},
+                                 OutCompactActive{nullptr, ptr<uint32_t>(c->sa_r), ptr<uint32_t>(c->g1),
+                                                  ptr<uint32_t>(c->p0), ptr<uint32_t>(c->v0), ptr<uint32_t>(c->g0)},
+                                 m, sm)));
+            TRY(read_words(c, sm, 1));
+            uint32_t na = c->h_pin[0], rounds = 0;
+            TRY(doubling_rounds(c, m, na, ptr<uint32_t>(c->v0), ptr<uint32_t>(c->v1), 1, &rounds));
             c->stats.doubling_rounds = rounds;
         }
         // K10: ranks -> text positions; the list is grouped by first byte by construction
@@ -400,10 +469,12 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
     if (n == 0) return B200SA_OK;
     uint32_t n32 = (uint32_t)n;
     TRY(ensure(c, c->isa, (size_t)n * 4));
-    TRY(mark(c, "lcp_isa"));
-    LAUNCH(c, k_isa, cdiv(n, BLK), d_sa, n32, ptr<uint32_t>(c->isa));
-    TRY(mark(c, "lcp_kasai"));
-    LAUNCH(c, k_lcp_kasai, cdiv(cdiv(n, LCP_CHUNK), BLK), d_text, n32, d_sa, ptr<uint32_t>(c->isa), d_lcp);
+    TRY(mark(c, "lcp_phi"));
+    LAUNCH(c, k_phi, cdiv(n, BLK), d_sa, n32, ptr<uint32_t>(c->isa));
+    TRY(mark(c, "lcp_plcp"));
+    LAUNCH(c, k_plcp, cdiv(cdiv(n, LCP_CHUNK), BLK), d_text, n32, ptr<uint32_t>(c->isa));
+    TRY(mark(c, "lcp_gather"));
+    LAUNCH(c, k_lcp_gather, cdiv(n, BLK), d_sa, ptr<uint32_t>(c->isa), n32, d_lcp);
     TRY(mark(c, "end"));
     CU_TRY(c, cudaGetLastError());
     return B200SA_OK;
@@ -465,6 +536,8 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
     if (!prop.cooperativeLaunch) { delete c; return B200SA_ERR_NO_DEVICE; }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_sa, cudaEventDisableTiming) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     if (cudaMallocHost((void **)&c->h_pin, 64 * sizeof(uint32_t)) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     int occL = 0, occS = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occL, k_induce<false>, BLK, 0);
@@ -491,6 +564,8 @@ void b200sa_ctx_destroy(b200sa_ctx *c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_sa) cudaEventDestroy(c->ev_sa);
     delete c;
 }
 
@@ -553,7 +628,13 @@ static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *
         TRY(build_dev(c, ptr<uint8_t>(c->text), n, ptr<uint32_t>(c->sa)));
         if (sa_out) {
             TRY(mark(c, "d2h_sa"));
-            CU_TRY(c, cudaMemcpyAsync(sa_out, c->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+            if (lcp_out) {      // the LCP kernels only read the SA: copy it out underneath them
+                CU_TRY(c, cudaEventRecord(c->ev_sa, c->stream));
+                CU_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_sa, 0));
+                CU_TRY(c, cudaMemcpyAsync(sa_out, c->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+            } else {
+                CU_TRY(c, cudaMemcpyAsync(sa_out, c->sa.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+            }
         }
     }
     if (lcp_out) {
@@ -564,6 +645,7 @@ static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *
     }
     TRY(mark(c, "end"));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->copy_stream));
     return end_call(c);
 }
 

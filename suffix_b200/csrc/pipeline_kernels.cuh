@@ -86,6 +86,25 @@ struct OutReduced {
     }
 };
 
+// Doubling start-up straight from the sorted LMS substrings (no re-sort of the
+// names): slot i of the reduced SA holds text_rank(sorted[i]); its group is the
+// run of equal names it sits in; rank[] plays the role of the reduced string
+// (reference P11-P12, src/table.rs:465-492, kept as ranks instead of names).
+struct InFlagPos {
+    const uint8_t *f;
+    __device__ uint32_t operator()(uint64_t i) const { return f[i] ? (uint32_t)i : 0u; }
+};
+struct OutInitFromSorted {
+    const uint32_t *sorted; const uint32_t *lmsb; const uint32_t *lmsrank;
+    uint32_t *sa_r; uint32_t *grp; uint32_t *rank;
+    __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const {
+        uint32_t g = exc > v ? exc : v;
+        uint32_t tr = lms_text_rank(lmsb, lmsrank, sorted[i]);
+        sa_r[i] = tr;
+        grp[i] = g;
+        rank[tr] = g + 1u;
+    }
+};
 // K9: all names unique -> SA of the reduced string is the inverse permutation
 __global__ void __launch_bounds__(BLK) k_invert_perm(const uint32_t *reduced, uint32_t m, uint32_t *sa_r) {
     uint32_t k = blockIdx.x * BLK + threadIdx.x;
@@ -102,6 +121,21 @@ __global__ void __launch_bounds__(BLK) k_unrename(const uint32_t *sa_r, const ui
 __global__ void __launch_bounds__(BLK) k_iota(uint32_t *a, uint32_t m) {
     uint32_t i = blockIdx.x * BLK + threadIdx.x;
     if (i < m) a[i] = i;
+}
+// Round-0 key of k consecutive symbols: sym+1 per slot (0 = beyond the end, so
+// a proper prefix sorts first), bw bits per slot, first symbol most significant.
+template <class K>
+__global__ void __launch_bounds__(BLK) k_multi_key(const uint32_t *__restrict__ R, uint32_t m, uint32_t k,
+                                                   uint32_t bw, K *keys) {
+    uint32_t i = blockIdx.x * BLK + threadIdx.x;
+    if (i >= m) return;
+    K key = 0;
+    for (uint32_t j = 0; j < k; j++) {
+        uint64_t p = (uint64_t)i + j;
+        K v = p < m ? (K)(__ldg(R + p) + 1u) : (K)0;
+        key = (key << bw) | v;
+    }
+    keys[i] = key;
 }
 template <class K>
 struct DigKey {
@@ -164,16 +198,21 @@ __global__ void __launch_bounds__(BLK) k_pair_keys(const uint32_t *agrp, const u
 }
 
 // ------------------------------------------------------------ LCP
-__global__ void __launch_bounds__(BLK) k_isa(const uint32_t *sa, uint32_t n, uint32_t *isa) {
-    uint32_t i = blockIdx.x * BLK + threadIdx.x;
-    if (i < n) isa[sa[i]] = i;
+// Phi / PLCP formulation of Kasai (same values as the reference's
+// lcp_lens_quadratic, src/table.rs:348-361; the algorithm is the byte-level
+// version of the commented-out lcp_lens_linear, :314-346):
+//   phi[sa[r]] = sa[r-1]            (one random write per suffix)
+//   plcp[i]    = lcp(i, phi[i])     (text order; plcp[i] >= plcp[i-1]-1)
+//   lcp[r]     = plcp[sa[r]]        (one random read per suffix)
+constexpr uint32_t PHI_NONE = 0xffffffffu;
+__global__ void __launch_bounds__(BLK) k_phi(const uint32_t *__restrict__ sa, uint32_t n, uint32_t *phi) {
+    uint32_t r = blockIdx.x * BLK + threadIdx.x;
+    if (r < n) phi[sa[r]] = r ? sa[r - 1] : PHI_NONE;
 }
-// Kasai over chunks of LCP_CHUNK consecutive text positions per thread: the
-// first position of a chunk starts from h=0, the rest reuse h-1.
+// One thread owns LCP_CHUNK consecutive text positions: the first starts from
+// h = 0, the rest reuse h-1.  buf holds phi on entry and plcp on exit.
 constexpr int LCP_CHUNK = 32;
-__global__ void __launch_bounds__(BLK) k_lcp_kasai(const uint8_t *__restrict__ text, uint32_t n,
-                                                   const uint32_t *__restrict__ sa,
-                                                   const uint32_t *__restrict__ isa, uint32_t *lcp) {
+__global__ void __launch_bounds__(BLK) k_plcp(const uint8_t *__restrict__ text, uint32_t n, uint32_t *buf) {
     uint64_t t = (uint64_t)blockIdx.x * BLK + threadIdx.x;
     uint64_t i0 = t * LCP_CHUNK;
     if (i0 >= n) return;
@@ -181,15 +220,19 @@ __global__ void __launch_bounds__(BLK) k_lcp_kasai(const uint8_t *__restrict__ t
     if (i1 > n) i1 = n;
     uint32_t h = 0;
     for (uint64_t i = i0; i < i1; i++) {
-        uint32_t r = isa[i];
-        if (r == 0) { lcp[0] = 0; h = 0; continue; }
-        uint32_t j = __ldg(sa + r - 1);
+        uint32_t j = buf[i];
+        if (j == PHI_NONE) { buf[i] = 0; h = 0; continue; }
         uint64_t a = i + h, b = (uint64_t)j + h;
         while (a < n && b < n && __ldg(text + a) == __ldg(text + b)) { a++; b++; }
         h = (uint32_t)(a - i);
-        lcp[r] = h;
+        buf[i] = h;
         if (h > 0) h--;
     }
+}
+__global__ void __launch_bounds__(BLK) k_lcp_gather(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ plcp,
+                                                    uint32_t n, uint32_t *lcp) {
+    uint32_t r = blockIdx.x * BLK + threadIdx.x;
+    if (r < n) lcp[r] = plcp[sa[r]];
 }
 
 // ------------------------------------------------------------ batched positions
