@@ -52,6 +52,7 @@ struct b200sa_ctx {
     DevBuf text, sa, lcp;                      // staging for the host API
     DevBuf pred, stype, lmsb, lmsrank, lmspos, lmslist, lmspred, sorted, flag, reduced, sa_r;
     DevBuf blkstate, carry, tables, small, scan_partial, radix_cnt, blkcnt;
+    DevBuf os_hist, os_status;
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
     uint64_t last_n = 0, last_m = 0;
 };
@@ -188,16 +189,34 @@ static int radix_pass(b200sa_ctx *c, DigF dig, MoveF mv, uint64_t n) {
     return B200SA_OK;
 }
 
-// Sorts (ka,va) by the low `bits` of the key; *kout/*vout point at the buffer
-// pair holding the result.
+// Sorts (ka,va) by the low `bits` of the key with the one-sweep passes of
+// common.cuh; *kout/*vout point at the buffer pair holding the result.
 template <class K>
 static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, uint64_t n, int bits,
                       K **kout, uint32_t **vout) {
-    for (int shift = 0; shift < bits; shift += 8) {
-        TRY(radix_pass(c, DigKey<K>{ka, (uint32_t)shift}, MoveKV<K>{ka, va, kb, vb}, n));
+    *kout = ka;
+    *vout = va;
+    if (n == 0 || bits <= 0) return B200SA_OK;
+    int npass = (bits + 7) / 8;
+    if (npass > OS_MAX_PASSES) npass = OS_MAX_PASSES;
+    uint32_t tiles = cdiv(n, TILE);
+    size_t status_bytes = (size_t)tiles * 256 * 8;
+    TRY(ensure(c, c->os_hist, OS_MAX_PASSES * 256 * 4 + 64));
+    TRY(ensure(c, c->os_status, status_bytes));
+    uint32_t *ghist = ptr<uint32_t>(c->os_hist);
+    uint32_t *ticket = ghist + OS_MAX_PASSES * 256;
+    CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
+    uint32_t hb = tiles < 1184u ? tiles : 1184u;
+    LAUNCH(c, (k_os_hist<K>), hb, ka, n, npass, ghist);
+    LAUNCH(c, k_os_scan, (uint32_t)npass, ghist);
+    for (int p = 0; p < npass; p++) {
+        CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
+        LAUNCH(c, (k_os_pass<K>), tiles, ka, va, kb, vb, n, (uint32_t)(8 * p), ghist + p * 256,
+               reinterpret_cast<volatile unsigned long long *>(c->os_status.p), ticket + p);
         K *tk = ka; ka = kb; kb = tk;
         uint32_t *tv = va; va = vb; vb = tv;
     }
+    CU_TRY(c, cudaGetLastError());
     *kout = ka;
     *vout = va;
     return B200SA_OK;
@@ -215,7 +234,8 @@ static int bit_length(uint64_t x) {
 // slots in c->p0 and group starts in c->g0; rank[] and sa_r hold the order by
 // the first h symbols.
 static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asuf, uint32_t *ascratch, uint64_t h,
-                           uint32_t *rounds_io) {
+                           uint32_t *rounds_io, const uint32_t *names_arr = nullptr, uint32_t kgram = 0,
+                           uint32_t bw = 0) {
     uint32_t *sa_r = ptr<uint32_t>(c->sa_r), *rank = ptr<uint32_t>(c->rank);
     uint32_t *apos = ptr<uint32_t>(c->p0), *apos_next = ptr<uint32_t>(c->p1);
     uint32_t *G0 = ptr<uint32_t>(c->g0), *G1 = ptr<uint32_t>(c->g1), *agrp = G0;
@@ -231,9 +251,16 @@ static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asu
         if (rounds > 40) { c->last_error = "doubling did not converge"; return B200SA_ERR_INTERNAL; }
         uint64_t *KA = ptr<uint64_t>(c->k64a), *KB = ptr<uint64_t>(c->k64b), *K2;
         uint32_t hh = h > 0xffffffffull ? 0xffffffffu : (uint32_t)h;
-        LAUNCH(c, k_pair_keys, cdiv(na, BLK), agrp, asuf, rank, na, m, hh, (uint32_t)b2, KA);
+        bool first = (names_arr != nullptr) && rounds == *rounds_io + 1 && kgram >= 2;
+        int bits = 2 * b2;
+        if (first) {     // depth 1 -> depth kgram in one sort of kgram dense names
+            LAUNCH(c, (k_multi_key_list<uint64_t>), cdiv(na, BLK), names_arr, m, asuf, na, kgram, bw, KA);
+            bits = (int)(kgram * bw);
+        } else {
+            LAUNCH(c, k_pair_keys, cdiv(na, BLK), agrp, asuf, rank, na, m, hh, (uint32_t)b2, KA);
+        }
         uint32_t *Vsorted;
-        TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, 2 * b2, &K2, &Vsorted));
+        TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, bits, &K2, &Vsorted));
         uint32_t *Vother = (Vsorted == asuf) ? ascratch : asuf;
         TRY((dev_scan<OpMax>(c, InGroupStart<uint64_t>{K2, apos}, OutGroupRank{Vsorted, apos, G1, rank, sa_r}, na, nullptr)));
         TRY((dev_scan<OpSum>(c, InActive<uint64_t>{K2, na}, OutCompactActive{apos, Vsorted, G1, apos_next, Vother, G0}, na, d_na)));
@@ -242,7 +269,7 @@ static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asu
         asuf = Vother; ascratch = Vsorted;
         uint32_t *t = apos; apos = apos_next; apos_next = t;
         agrp = G0;
-        h *= 2;
+        if (first) h = kgram; else h *= 2;
     }
     *rounds_io = rounds;
     return B200SA_OK;
@@ -409,7 +436,9 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
         TRY(mark(c, "name"));
         LAUNCH(c, k_name_flags, cdiv(m, BLK), text, n32, ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb),
                ptr<uint32_t>(c->sorted), m, ptr<uint8_t>(c->flag));
-        TRY((dev_reduce<OpSum>(c, InFlagU8{ptr<uint8_t>(c->flag)}, m, sm + 2)));
+        TRY((dev_scan<OpSum>(c, InFlagU8{ptr<uint8_t>(c->flag)},
+                             OutReduced{ptr<uint32_t>(c->sorted), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank), ptr<uint32_t>(c->reduced)},
+                             m, sm + 2)));
         TRY(read_words(c, sm + 1, 2));
         uint32_t cnt_lms = c->h_pin[0], names = c->h_pin[1];
         if (cnt_lms != m) {
@@ -440,7 +469,13 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
                                  m, sm)));
             TRY(read_words(c, sm, 1));
             uint32_t na = c->h_pin[0], rounds = 0;
-            TRY(doubling_rounds(c, m, na, ptr<uint32_t>(c->v0), ptr<uint32_t>(c->v1), 1, &rounds));
+            // first refinement: k-gram of dense names (reduced string), k = as many as fit 64 bits
+            uint32_t bw = (uint32_t)bit_length(names);
+            uint32_t kgram = bw ? 64u / bw : 0u;
+            if (kgram > 8) kgram = 8;
+            if (const char *e = getenv("B200SA_KGRAM")) { int v = atoi(e); if (v >= 0 && (uint32_t)v * bw <= 64) kgram = (uint32_t)v; }
+            TRY(doubling_rounds(c, m, na, ptr<uint32_t>(c->v0), ptr<uint32_t>(c->v1), 1, &rounds,
+                                ptr<uint32_t>(c->reduced), kgram, bw));
             c->stats.doubling_rounds = rounds;
         }
         // K10: ranks -> text positions; the list is grouped by first byte by construction
@@ -559,7 +594,7 @@ void b200sa_ctx_destroy(b200sa_ctx *c) {
     DevBuf *bufs[] = {&c->text, &c->sa, &c->lcp, &c->pred, &c->stype, &c->lmsb, &c->lmsrank, &c->lmspos, &c->lmslist,
                       &c->lmspred, &c->sorted, &c->flag, &c->reduced, &c->sa_r, &c->blkstate, &c->carry, &c->tables,
                       &c->small, &c->scan_partial, &c->radix_cnt, &c->blkcnt, &c->k32b, &c->k64a, &c->k64b, &c->v0,
-                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf};
+                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);

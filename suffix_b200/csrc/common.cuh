@@ -253,3 +253,111 @@ __global__ void __launch_bounds__(BLK) k_radix_scatter(DigF dig, MoveF mv, uint6
 }
 
 }  // namespace b200sa
+
+// ---------------------------------------------------------------- one-sweep LSD radix sort
+// (key,u32 value) pairs, 8-bit digits.  One upfront kernel builds the digit
+// histograms of ALL passes; each pass then reads the data once: tiles are
+// claimed in order through an atomic ticket, per-tile digit counts are chained
+// with decoupled look-back (64-bit status words: flag in bits 62-63, count in
+// the low 32), and the tile is staged through shared memory in digit order so
+// that the global writes are contiguous runs.
+namespace b200sa {
+
+constexpr unsigned long long OS_AGG = 1ull << 62, OS_INCL = 2ull << 62, OS_VAL = 0xffffffffull;
+constexpr int OS_MAX_PASSES = 8;
+
+template <class K>
+__global__ void __launch_bounds__(BLK) k_os_hist(const K *__restrict__ keys, uint64_t n, int npass, uint32_t *ghist) {
+    __shared__ uint32_t s_h[OS_MAX_PASSES][256];
+    for (int p = 0; p < npass; p++) s_h[p][threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i0 = (uint64_t)blockIdx.x * BLK; i0 < n; i0 += (uint64_t)gridDim.x * BLK) {
+        uint64_t i = i0 + threadIdx.x;
+        bool valid = i < n;
+        K key = valid ? keys[i] : (K)0;
+        for (int p = 0; p < npass; p++) hist_add(s_h[p], (uint32_t)(key >> (8 * p)) & 0xffu, valid);
+    }
+    __syncthreads();
+    for (int p = 0; p < npass; p++) {
+        uint32_t v = s_h[p][threadIdx.x];
+        if (v) atomicAdd(&ghist[p * 256 + threadIdx.x], v);
+    }
+}
+
+// one block per pass: exclusive scan of its 256 digit totals, in place
+__global__ void __launch_bounds__(BLK) k_os_scan(uint32_t *ghist) {
+    __shared__ uint32_t s_w[NWARP + 1];
+    uint32_t v = ghist[blockIdx.x * 256 + threadIdx.x], total;
+    uint32_t inc = block_incl_scan<OpSum>(v, s_w, &total);
+    ghist[blockIdx.x * 256 + threadIdx.x] = inc - v;
+}
+
+template <class K>
+__global__ void __launch_bounds__(BLK) k_os_pass(const K *__restrict__ kin, const uint32_t *__restrict__ vin, K *kout,
+                                                 uint32_t *vout, uint64_t n, uint32_t shift,
+                                                 const uint32_t *__restrict__ gbase, volatile unsigned long long *status,
+                                                 uint32_t *ticket) {
+    __shared__ uint32_t s_wcnt[NWARP][256];
+    __shared__ uint32_t s_tcnt[256], s_texcl[256], s_gb[256];
+    __shared__ uint32_t s_w[NWARP + 1];
+    __shared__ K s_k[TILE];
+    __shared__ uint32_t s_v[TILE];
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int ww = 0; ww < NWARP; ww++) s_wcnt[ww][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile, w = warp_id(), l = lane_id();
+    const uint64_t tb = (uint64_t)tile * TILE;
+    K key[ITEMS];
+    uint32_t val[ITEMS], d[ITEMS], rank[ITEMS], vm = 0;
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        uint64_t i = tb + (uint64_t)w * (ITEMS * 32) + r * 32 + l;
+        bool valid = i < n;
+        key[r] = valid ? kin[i] : (K)0;
+        val[r] = valid ? vin[i] : 0u;
+        d[r] = (uint32_t)(key[r] >> shift) & 0xffu;
+        vm |= (valid ? 1u : 0u) << r;
+    }
+    tile_rank(d, vm, rank, s_wcnt, s_tcnt);
+    {
+        const uint32_t dg = threadIdx.x;
+        uint32_t cnt = s_tcnt[dg], total;
+        uint32_t inc = block_incl_scan<OpSum>(cnt, s_w, &total);
+        uint32_t texcl = inc - cnt;
+        s_texcl[dg] = texcl;
+        volatile unsigned long long *mine = status + (uint64_t)tile * 256 + dg;
+        *mine = OS_AGG | cnt;
+        uint32_t excl = 0;
+        for (uint32_t t = tile; t-- > 0;) {
+            volatile unsigned long long *q = status + (uint64_t)t * 256 + dg;
+            unsigned long long v;
+            do { v = *q; } while ((v >> 62) == 0);
+            excl += (uint32_t)(v & OS_VAL);
+            if ((v >> 62) == 2) break;
+        }
+        *mine = OS_INCL | (unsigned long long)(excl + cnt);
+        s_gb[dg] = gbase[dg] + excl - texcl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        if ((vm >> r) & 1u) {
+            uint32_t p = s_texcl[d[r]] + s_wcnt[w][d[r]] + rank[r];
+            s_k[p] = key[r];
+            s_v[p] = val[r];
+        }
+    }
+    __syncthreads();
+    uint64_t left = n - tb;
+    uint32_t cnt_tile = left < (uint64_t)TILE ? (uint32_t)left : (uint32_t)TILE;
+    for (uint32_t j = threadIdx.x; j < cnt_tile; j += BLK) {
+        K k = s_k[j];
+        uint32_t dst = s_gb[(uint32_t)(k >> shift) & 0xffu] + j;
+        kout[dst] = k;
+        vout[dst] = s_v[j];
+    }
+}
+
+}  // namespace b200sa

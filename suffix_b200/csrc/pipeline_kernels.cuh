@@ -137,6 +137,23 @@ __global__ void __launch_bounds__(BLK) k_multi_key(const uint32_t *__restrict__ 
     }
     keys[i] = key;
 }
+// Same key for a list of suffixes (first refinement round: jumps from depth 1
+// to depth k in one sort).
+template <class K>
+__global__ void __launch_bounds__(BLK) k_multi_key_list(const uint32_t *__restrict__ R, uint32_t m,
+                                                        const uint32_t *__restrict__ suf, uint32_t na, uint32_t k,
+                                                        uint32_t bw, K *keys) {
+    uint32_t idx = blockIdx.x * BLK + threadIdx.x;
+    if (idx >= na) return;
+    uint32_t i = suf[idx];
+    K key = 0;
+    for (uint32_t j = 0; j < k; j++) {
+        uint64_t p = (uint64_t)i + j;
+        K v = p < m ? (K)(__ldg(R + p) + 1u) : (K)0;
+        key = (key << bw) | v;
+    }
+    keys[idx] = key;
+}
 template <class K>
 struct DigKey {
     const K *keys; uint32_t shift;
