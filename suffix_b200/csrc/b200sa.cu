@@ -36,7 +36,10 @@ struct b200sa_ctx {
     cudaStream_t copy_stream = nullptr;   // D2H of the SA overlapped with the LCP kernels
     cudaEvent_t ev_sa = nullptr;
     int sm_count = 0;
-    int induce_blocks = 0;
+    int induce_blocks = 0;          // largest co-resident grid (workspace is sized for it)
+    int induce_bps_max = 1;         // occupancy bound, blocks per SM
+    int induce_bps_env = 0;         // B200SA_INDUCE_BPS override (0 = adaptive)
+    int cur_induce_blocks = 0;      // grid of the current build
     std::string last_error;
     bool timing = false;
     std::vector<std::pair<const char *, cudaEvent_t>> marks;
@@ -52,10 +55,17 @@ struct b200sa_ctx {
     DevBuf text, sa, lcp;                      // staging for the host API
     DevBuf pred, stype, lmsb, lmsrank, lmspos, lmslist, lmspred, sorted, flag, reduced, sa_r;
     DevBuf blkstate, carry, tables, small, scan_partial, radix_cnt, blkcnt;
-    DevBuf os_hist, os_status;
+    DevBuf os_hist, os_status, phik, phiv;
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
+    DevBuf packed;
+    int bits = 8;                    // bits per char of the packed text of the current call (2, 4 or 8 = raw)
+    const void *ptext = nullptr;     // packed words, or the byte text when bits == 8
     uint64_t last_n = 0, last_m = 0;
 };
+
+// layout of the `tables` buffer (u32 words)
+constexpr int T_BSTART = 0, T_LCNT = 257, T_SCNT = 513, T_LMSOFF = 769, T_HIST = 1026, T_CODE = 1794,
+              T_ALPHA = 2050, T_END = 2306;
 
 static const char *kVersion = "b200sa 0.1 (sm_100a)";
 
@@ -207,11 +217,12 @@ static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, u
     uint32_t *ticket = ghist + OS_MAX_PASSES * 256;
     CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
     uint32_t hb = tiles < 1184u ? tiles : 1184u;
-    LAUNCH(c, (k_os_hist<K>), hb, ka, n, npass, ghist);
+    LAUNCH(c, (k_os_hist<K, LoadArr<K>>), hb, LoadArr<K>{ka}, n, npass, 0u, ghist);
     LAUNCH(c, k_os_scan, (uint32_t)npass, ghist);
     for (int p = 0; p < npass; p++) {
         CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
-        LAUNCH(c, (k_os_pass<K>), tiles, ka, va, kb, vb, n, (uint32_t)(8 * p), ghist + p * 256,
+        LAUNCH(c, (k_os_pass<K, LoadArr<K>, LoadArr<uint32_t>>), tiles, LoadArr<K>{ka}, LoadArr<uint32_t>{va}, kb, vb, n,
+               (uint32_t)(8 * p), ghist + p * 256,
                reinterpret_cast<volatile unsigned long long *>(c->os_status.p), ticket + p);
         K *tk = ka; ka = kb; kb = tk;
         uint32_t *tv = va; va = vb; vb = tv;
@@ -246,8 +257,11 @@ static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asu
         TRY(ensure(c, c->k64b, (size_t)na * 8));
     }
     int b2 = bit_length(m);
+    static const char *kSortNames[] = {"rsa_sort1", "rsa_sort2", "rsa_sort3", "rsa_sort4", "rsa_sort5", "rsa_sortN"};
+    static const char *kScanNames[] = {"rsa_scan1", "rsa_scan2", "rsa_scan3", "rsa_scan4", "rsa_scan5", "rsa_scanN"};
     while (na > 0) {
         rounds++;
+        { uint32_t ri = rounds - *rounds_io; TRY(mark(c, kSortNames[ri <= 5 ? ri - 1 : 5])); }
         if (rounds > 40) { c->last_error = "doubling did not converge"; return B200SA_ERR_INTERNAL; }
         uint64_t *KA = ptr<uint64_t>(c->k64a), *KB = ptr<uint64_t>(c->k64b), *K2;
         uint32_t hh = h > 0xffffffffull ? 0xffffffffu : (uint32_t)h;
@@ -262,10 +276,12 @@ static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asu
         uint32_t *Vsorted;
         TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, bits, &K2, &Vsorted));
         uint32_t *Vother = (Vsorted == asuf) ? ascratch : asuf;
+        { uint32_t ri = rounds - *rounds_io; TRY(mark(c, kScanNames[ri <= 5 ? ri - 1 : 5])); }
         TRY((dev_scan<OpMax>(c, InGroupStart<uint64_t>{K2, apos}, OutGroupRank{Vsorted, apos, G1, rank, sa_r}, na, nullptr)));
         TRY((dev_scan<OpSum>(c, InActive<uint64_t>{K2, na}, OutCompactActive{apos, Vsorted, G1, apos_next, Vother, G0}, na, d_na)));
         TRY(read_words(c, d_na, 1));
         na = c->h_pin[0];
+        if (getenv("B200SA_TRACE")) fprintf(stderr, "[b200sa] doubling round %u: h=%llu -> active %u of %u\n", rounds, (unsigned long long)h, na, m);
         asuf = Vother; ascratch = Vsorted;
         uint32_t *t = apos; apos = apos_next; apos_next = t;
         agrp = G0;
@@ -339,21 +355,45 @@ static int reduced_sa(b200sa_ctx *c, uint32_t *R, uint32_t m, uint32_t names, ui
     return B200SA_OK;
 }
 
+// ------------------------------------------------------- packed text
+// Chooses 2 / 4 bits per char when the alphabet allows it and packs the text;
+// code_of/alpha live in the tables buffer.
+static int pack_text(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t sigma) {
+    uint32_t *tab = ptr<uint32_t>(c->tables);
+    c->bits = 8;
+    c->ptext = text;
+    if (getenv("B200SA_NOPACK")) return B200SA_OK;
+    if (sigma <= 4) c->bits = 2; else if (sigma <= 16) c->bits = 4; else return B200SA_OK;
+    uint32_t cpw = 32 / c->bits;
+    uint64_t words = (n + cpw - 1) / cpw;
+    TRY(ensure(c, c->packed, words * 4 + 8));   // + one padding word for text_bits()
+    if (c->bits == 2) LAUNCH(c, (k_pack<2>), cdiv(words, BLK), text, n, tab + T_CODE, ptr<uint32_t>(c->packed));
+    else LAUNCH(c, (k_pack<4>), cdiv(words, BLK), text, n, tab + T_CODE, ptr<uint32_t>(c->packed));
+    CU_TRY(c, cudaGetLastError());
+    c->ptext = c->packed.p;
+    return B200SA_OK;
+}
+
 // ------------------------------------------------------- induce launcher
+static const void *induce_fn(bool spass, int bits) {
+    if (bits == 2) return spass ? (const void *)k_induce<true, 2> : (const void *)k_induce<false, 2>;
+    if (bits == 4) return spass ? (const void *)k_induce<true, 4> : (const void *)k_induce<false, 4>;
+    return spass ? (const void *)k_induce<true, 8> : (const void *)k_induce<false, 8>;
+}
 static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_t n, uint32_t *sa,
                          const uint32_t *lms, uint32_t m) {
     (void)m;
     uint32_t *tab = ptr<uint32_t>(c->tables);
     InduceArgs A;
-    A.text = text; A.n = n; A.sa = sa; A.pred = ptr<uint8_t>(c->pred);
+    A.text = text; A.ptext = c->ptext; A.alpha = tab + T_ALPHA;
+    A.n = n; A.sa = sa; A.pred = ptr<uint8_t>(c->pred);
     A.lms = lms; A.lms_pred = ptr<uint8_t>(c->lmspred);
-    A.bstart = tab; A.Lcnt = tab + 257; A.Scnt = tab + 257 + 256; A.lms_off = tab + 257 + 512;
+    A.bstart = tab + T_BSTART; A.Lcnt = tab + T_LCNT; A.Scnt = tab + T_SCNT; A.lms_off = tab + T_LMSOFF;
     A.blk_cnt = ptr<uint32_t>(c->blkcnt);
     uint32_t *sm = ptr<uint32_t>(c->small);
     A.g_fill = sm + 64; A.g_state = reinterpret_cast<int32_t *>(sm + 320); A.err = sm + 32;
     void *args[] = {&A};
-    const void *fn = spass ? (const void *)k_induce<true> : (const void *)k_induce<false>;
-    CU_TRY(c, cudaLaunchCooperativeKernel(fn, dim3(c->induce_blocks), dim3(BLK), args, 0, c->stream));
+    CU_TRY(c, cudaLaunchCooperativeKernel(induce_fn(spass, c->bits), dim3(c->cur_induce_blocks), dim3(BLK), args, 0, c->stream));
     c->launches++;
     return B200SA_OK;
 }
@@ -367,21 +407,30 @@ static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t
     TRY(ensure(c, c->lmsrank, nw * 4));
     TRY(ensure(c, c->blkstate, nbc));
     TRY(ensure(c, c->carry, nbc));
-    TRY(ensure(c, c->tables, (257 + 256 + 256 + 257 + 768) * 4));
+    TRY(ensure(c, c->tables, T_END * 4));
     TRY(ensure(c, c->small, 4096));
     uint32_t *tab = ptr<uint32_t>(c->tables);
-    uint32_t *hist = tab + 257 + 512 + 257;
+    uint32_t *hist = tab + T_HIST;
     uint32_t *sm = ptr<uint32_t>(c->small);
     CU_TRY(c, cudaMemsetAsync(hist, 0, 768 * 4, c->stream));
     CU_TRY(c, cudaMemsetAsync(sm, 0, 4096, c->stream));
     LAUNCH(c, k_cls_block_state, nbc, text, n, ptr<uint8_t>(c->blkstate));
     LAUNCH(c, k_cls_carry, 1, ptr<uint8_t>(c->blkstate), nbc, ptr<uint8_t>(c->carry));
     LAUNCH(c, k_cls_types, nbc, text, n, ptr<uint8_t>(c->carry), ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb), hist);
-    LAUNCH(c, k_bucket_tables, 1, hist, tab, tab + 257, tab + 257 + 256, tab + 257 + 512);
+    LAUNCH(c, k_bucket_tables, 1, hist, tab + T_BSTART, tab + T_LCNT, tab + T_SCNT, tab + T_LMSOFF, tab + T_CODE,
+           tab + T_ALPHA, sm + 3);
     CU_TRY(c, cudaGetLastError());
     TRY((dev_scan<OpSum>(c, InPopcWords{ptr<uint32_t>(c->lmsb)}, OutStoreExcl{ptr<uint32_t>(c->lmsrank)}, nw, sm)));
-    TRY(read_words(c, sm, 1));
-    uint32_t m = c->h_pin[0];
+    TRY(read_words(c, sm, 4));
+    uint32_t m = c->h_pin[0], sigma = c->h_pin[3];
+    TRY(pack_text(c, text, n, sigma));
+    {   // grid of the persistent induce kernels: few buckets -> long lists, latency bound -> more blocks
+        // per SM; many buckets -> grid-sync bound -> one block per SM
+        int bps = sigma <= 16 ? 3 : (sigma <= 64 ? 2 : 1);
+        if (c->induce_bps_env) bps = c->induce_bps_env;
+        if (bps > c->induce_bps_max) bps = c->induce_bps_max;
+        c->cur_induce_blocks = c->sm_count * bps;
+    }
     TRY(ensure(c, c->lmspos, (size_t)m * 4));
     if (m > 0) {
         LAUNCH(c, k_lms_positions, cdiv(nw, BLK), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank), nw, ptr<uint32_t>(c->lmspos));
@@ -395,7 +444,7 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     memset(&c->stats, 0, sizeof c->stats);
     c->stats.n = n;
     c->stats.sm_count = c->sm_count;
-    c->stats.induce_blocks = c->induce_blocks;
+    c->stats.induce_blocks = c->induce_blocks;   // updated after classification
     c->last_n = n; c->last_m = 0;
     if (n > 0xFFFFFFFFull) { c->last_error = "text longer than 2^32-1 bytes"; return B200SA_ERR_TOO_LARGE; }
     if (n == 0) return B200SA_OK;
@@ -411,6 +460,7 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     uint32_t m = 0;
     TRY(classify_dev(c, text, n, &m));
     c->stats.m = m; c->last_m = m;
+    c->stats.induce_blocks = c->cur_induce_blocks;
     TRY(ensure(c, c->pred, n));
     TRY(ensure(c, c->lmslist, (size_t)m * 4));
     TRY(ensure(c, c->lmspred, m));
@@ -434,8 +484,15 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
         TRY((dev_scan<OpSum>(c, InIsLmsEntry{d_sa, ptr<uint32_t>(c->lmsb)}, OutCompactSa{d_sa, ptr<uint32_t>(c->sorted)}, n, sm + 1)));
         // K7/K8: names, reduced string
         TRY(mark(c, "name"));
-        LAUNCH(c, k_name_flags, cdiv(m, BLK), text, n32, ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb),
-               ptr<uint32_t>(c->sorted), m, ptr<uint8_t>(c->flag));
+        if (c->bits == 2)
+            LAUNCH(c, (k_name_flags<2>), cdiv(m, BLK), c->ptext, n32, ptr<uint32_t>(c->lmsb),
+                   ptr<uint32_t>(c->sorted), m, ptr<uint8_t>(c->flag));
+        else if (c->bits == 4)
+            LAUNCH(c, (k_name_flags<4>), cdiv(m, BLK), c->ptext, n32, ptr<uint32_t>(c->lmsb),
+                   ptr<uint32_t>(c->sorted), m, ptr<uint8_t>(c->flag));
+        else
+            LAUNCH(c, (k_name_flags<8>), cdiv(m, BLK), c->ptext, n32, ptr<uint32_t>(c->lmsb),
+                   ptr<uint32_t>(c->sorted), m, ptr<uint8_t>(c->flag));
         TRY((dev_scan<OpSum>(c, InFlagU8{ptr<uint8_t>(c->flag)},
                              OutReduced{ptr<uint32_t>(c->sorted), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank), ptr<uint32_t>(c->reduced)},
                              m, sm + 2)));
@@ -499,15 +556,61 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     return B200SA_OK;
 }
 
-static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa, uint32_t *d_lcp) {
+static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa, uint32_t *d_lcp,
+                   bool reuse_pack) {
     if (n > 0xFFFFFFFFull) return B200SA_ERR_TOO_LARGE;
     if (n == 0) return B200SA_OK;
     uint32_t n32 = (uint32_t)n;
     TRY(ensure(c, c->isa, (size_t)n * 4));
+    if (!reuse_pack) {
+        // stand-alone call: byte histogram -> alphabet -> packed text
+        TRY(mark(c, "lcp_pack"));
+        const uint8_t *text = d_text;
+        if (((uintptr_t)d_text & 15) != 0) {
+            TRY(ensure(c, c->text, n));
+            CU_TRY(c, cudaMemcpyAsync(c->text.p, d_text, n, cudaMemcpyDeviceToDevice, c->stream));
+            text = ptr<uint8_t>(c->text);
+        }
+        TRY(ensure(c, c->tables, T_END * 4));
+        TRY(ensure(c, c->small, 4096));
+        uint32_t *tab = ptr<uint32_t>(c->tables), *sm = ptr<uint32_t>(c->small);
+        CU_TRY(c, cudaMemsetAsync(tab + T_HIST, 0, 256 * 4, c->stream));
+        uint32_t hb = cdiv(n, BLK * 64);
+        if (hb > 1184) hb = 1184;
+        LAUNCH(c, k_byte_hist, hb, text, n, tab + T_HIST);
+        LAUNCH(c, k_alpha_from_hist, 1, tab + T_HIST, tab + T_CODE, tab + T_ALPHA, sm + 3);
+        TRY(read_words(c, sm + 3, 1));
+        TRY(pack_text(c, text, n, c->h_pin[0]));
+    }
     TRY(mark(c, "lcp_phi"));
-    LAUNCH(c, k_phi, cdiv(n, BLK), d_sa, n32, ptr<uint32_t>(c->isa));
+    if (n >= (1u << 22) && !getenv("B200SA_PHI_DIRECT")) {
+        // partition (sa[r], sa[r-1]) by the top byte of sa[r], then scatter window by window
+        TRY(ensure(c, c->phik, (size_t)n * 4));
+        TRY(ensure(c, c->phiv, (size_t)n * 4));
+        TRY(ensure(c, c->os_hist, OS_MAX_PASSES * 256 * 4 + 64));
+        uint32_t tiles = cdiv(n, TILE);
+        size_t status_bytes = (size_t)tiles * 256 * 8;
+        TRY(ensure(c, c->os_status, status_bytes));
+        uint32_t *ghist = ptr<uint32_t>(c->os_hist), *ticket = ghist + OS_MAX_PASSES * 256;
+        int nbits = bit_length(n - 1);
+        uint32_t shift = nbits > 8 ? (uint32_t)(nbits - 8) : 0u;
+        CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
+        CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
+        uint32_t hb = tiles < 1184u ? tiles : 1184u;
+        LAUNCH(c, (k_os_hist<uint32_t, LoadArr<uint32_t>>), hb, LoadArr<uint32_t>{d_sa}, n, 1, shift, ghist);
+        LAUNCH(c, k_os_scan, 1u, ghist);
+        LAUNCH(c, (k_os_pass<uint32_t, LoadArr<uint32_t>, LoadPhiPrev>), tiles, LoadArr<uint32_t>{d_sa}, LoadPhiPrev{d_sa},
+               ptr<uint32_t>(c->phik), ptr<uint32_t>(c->phiv), n, shift, ghist,
+               reinterpret_cast<volatile unsigned long long *>(c->os_status.p), ticket);
+        LAUNCH(c, k_phi_apply, cdiv(n, BLK), ptr<uint32_t>(c->phik), ptr<uint32_t>(c->phiv), n32, ptr<uint32_t>(c->isa));
+    } else {
+        LAUNCH(c, k_phi, cdiv(n, BLK), d_sa, n32, ptr<uint32_t>(c->isa));
+    }
     TRY(mark(c, "lcp_plcp"));
-    LAUNCH(c, k_plcp, cdiv(cdiv(n, LCP_CHUNK), BLK), d_text, n32, ptr<uint32_t>(c->isa));
+    uint32_t pg = cdiv(cdiv(n, LCP_CHUNK), BLK);
+    if (c->bits == 2) LAUNCH(c, (k_plcp<2>), pg, c->ptext, n32, ptr<uint32_t>(c->isa));
+    else if (c->bits == 4) LAUNCH(c, (k_plcp<4>), pg, c->ptext, n32, ptr<uint32_t>(c->isa));
+    else LAUNCH(c, (k_plcp<8>), pg, c->ptext, n32, ptr<uint32_t>(c->isa));
     TRY(mark(c, "lcp_gather"));
     LAUNCH(c, k_lcp_gather, cdiv(n, BLK), d_sa, ptr<uint32_t>(c->isa), n32, d_lcp);
     TRY(mark(c, "end"));
@@ -568,21 +671,28 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     c->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("B200SA_L2FETCH")) {   // experiment: L2 fetch granularity for random gathers
+        int v = atoi(e);
+        if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+    }
     if (!prop.cooperativeLaunch) { delete c; return B200SA_ERR_NO_DEVICE; }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     c->stream = c->own_stream;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_sa, cudaEventDisableTiming) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     if (cudaMallocHost((void **)&c->h_pin, 64 * sizeof(uint32_t)) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
-    int occL = 0, occS = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occL, k_induce<false>, BLK, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, k_induce<true>, BLK, 0);
-    int occ = occL < occS ? occL : occS;
+    int occ = 1 << 30;
+    for (int sp = 0; sp < 2; sp++)
+        for (int b : {2, 4, 8}) {
+            int o = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, induce_fn(sp != 0, b), BLK, 0);
+            if (o < occ) occ = o;
+        }
     if (occ < 1) { cudaFreeHost(c->h_pin); delete c; return B200SA_ERR_CUDA; }
-    int bps = 2;
-    if (const char *e = getenv("B200SA_INDUCE_BPS")) { int v = atoi(e); if (v >= 1) bps = v; }
-    if (bps > occ) bps = occ;
-    c->induce_blocks = c->sm_count * bps;
+    c->induce_bps_max = occ > 4 ? 4 : occ;
+    if (const char *e = getenv("B200SA_INDUCE_BPS")) { int v = atoi(e); if (v >= 1) c->induce_bps_env = v > occ ? occ : v; }
+    c->induce_blocks = c->sm_count * c->induce_bps_max;
+    c->cur_induce_blocks = c->sm_count;
     memset(&c->stats, 0, sizeof c->stats);
     *out = c;
     return B200SA_OK;
@@ -594,7 +704,7 @@ void b200sa_ctx_destroy(b200sa_ctx *c) {
     DevBuf *bufs[] = {&c->text, &c->sa, &c->lcp, &c->pred, &c->stype, &c->lmsb, &c->lmsrank, &c->lmspos, &c->lmslist,
                       &c->lmspred, &c->sorted, &c->flag, &c->reduced, &c->sa_r, &c->blkstate, &c->carry, &c->tables,
                       &c->small, &c->scan_partial, &c->radix_cnt, &c->blkcnt, &c->k32b, &c->k64a, &c->k64b, &c->v0,
-                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status};
+                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -641,7 +751,7 @@ int b200sa_lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
     if (!c || (n > 0 && (!d_text || !d_sa || !d_lcp))) return B200SA_ERR_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
     begin_call(c, stream);
-    int rc = lcp_dev(c, d_text, n, d_sa, d_lcp);
+    int rc = lcp_dev(c, d_text, n, d_sa, d_lcp, false);
     if (rc == B200SA_OK) rc = end_call(c);
     return rc;
 }
@@ -674,7 +784,7 @@ static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *
     }
     if (lcp_out) {
         TRY(ensure(c, c->lcp, (size_t)n * 4));
-        TRY(lcp_dev(c, ptr<uint8_t>(c->text), n, ptr<uint32_t>(c->sa), ptr<uint32_t>(c->lcp)));
+        TRY(lcp_dev(c, ptr<uint8_t>(c->text), n, ptr<uint32_t>(c->sa), ptr<uint32_t>(c->lcp), sa_in == nullptr && n >= 2));
         TRY(mark(c, "d2h_lcp"));
         CU_TRY(c, cudaMemcpyAsync(lcp_out, c->lcp.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -726,7 +836,7 @@ int b200sa_test_classify(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_
     uint64_t nw = (n + 31) / 32;
     if (stype_words) CU_TRY(c, cudaMemcpyAsync(stype_words, c->stype.p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
     if (lms_words) CU_TRY(c, cudaMemcpyAsync(lms_words, c->lmsb.p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (hist768) CU_TRY(c, cudaMemcpyAsync(hist768, ptr<uint32_t>(c->tables) + 257 + 512 + 257, 768 * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (hist768) CU_TRY(c, cudaMemcpyAsync(hist768, ptr<uint32_t>(c->tables) + T_HIST, 768 * 4, cudaMemcpyDeviceToHost, c->stream));
     if (lmspos && m > 0) {
         uint64_t k = m < cap_lms ? m : cap_lms;
         CU_TRY(c, cudaMemcpyAsync(lmspos, c->lmspos.p, k * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -787,7 +897,7 @@ int64_t b200sa_debug_fetch(b200sa_ctx *c, int which, void *out, uint64_t cap) {
         case 3: src = c->sa_r.p; count = c->last_m; break;
         case 4: src = c->lmslist.p; count = c->last_m; break;
         case 5: src = c->small.p ? (const void *)(ptr<uint32_t>(c->small) + 32) : nullptr; count = 4; break;
-        case 6: src = c->tables.p; count = 257 + 256 + 256 + 257; break;
+        case 6: src = c->tables.p; count = T_HIST; break;
         default: return B200SA_ERR_BAD_ARG;
     }
     if (!src) return 0;

@@ -176,9 +176,12 @@ __global__ void __launch_bounds__(BLK) k_cls_types(const uint8_t *__restrict__ t
 
 // K2: bucket tables from the histogram (single block).
 //   bstart[c] = start of bucket c in SA (bstart[256] = n)
-//   Lcnt/Scnt = type-split bucket sizes, lms_off = LMS group offsets.
+//   Lcnt/Scnt = type-split bucket sizes, lms_off = LMS group offsets,
+//   code_of[c] = rank of byte c among the bytes that occur (order preserving),
+//   alpha[code] = byte, *sigma = number of distinct bytes.
 __global__ void __launch_bounds__(BLK) k_bucket_tables(const uint32_t *hist768, uint32_t *bstart, uint32_t *Lcnt,
-                                                       uint32_t *Scnt, uint32_t *lms_off) {
+                                                       uint32_t *Scnt, uint32_t *lms_off, uint32_t *code_of,
+                                                       uint32_t *alpha, uint32_t *sigma) {
     __shared__ uint32_t s_w[NWARP + 1];
     uint32_t c = threadIdx.x;
     uint32_t L = hist768[c], S = hist768[256 + c] + hist768[512 + c], M = hist768[512 + c];
@@ -190,6 +193,130 @@ __global__ void __launch_bounds__(BLK) k_bucket_tables(const uint32_t *hist768, 
     inc = block_incl_scan<OpSum>(M, s_w, &total);
     lms_off[c] = inc - M;
     if (c == 255) lms_off[256] = total;
+    uint32_t present = (L + S) > 0 ? 1u : 0u;
+    inc = block_incl_scan<OpSum>(present, s_w, &total);
+    uint32_t code = inc - present;
+    code_of[c] = code;
+    alpha[c] = 0;
+    __syncthreads();
+    if (present) alpha[code] = c;
+    if (c == 0) *sigma = total;
+}
+
+// Standalone byte histogram (for b200sa_lcp_dev, which has no classification).
+__global__ void __launch_bounds__(BLK) k_byte_hist(const uint8_t *__restrict__ text, uint64_t n, uint32_t *hist256) {
+    __shared__ uint32_t s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i0 = (uint64_t)blockIdx.x * BLK; i0 < n; i0 += (uint64_t)gridDim.x * BLK) {
+        uint64_t i = i0 + threadIdx.x;
+        bool valid = i < n;
+        hist_add(s_h, valid ? (uint32_t)__ldg(text + i) : 0u, valid);
+    }
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(&hist256[threadIdx.x], s_h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(BLK) k_alpha_from_hist(const uint32_t *hist256, uint32_t *code_of, uint32_t *alpha,
+                                                         uint32_t *sigma) {
+    __shared__ uint32_t s_w[NWARP + 1];
+    uint32_t c = threadIdx.x, total;
+    uint32_t present = hist256[c] > 0 ? 1u : 0u;
+    uint32_t inc = block_incl_scan<OpSum>(present, s_w, &total);
+    uint32_t code = inc - present;
+    code_of[c] = code;
+    alpha[c] = 0;
+    __syncthreads();
+    if (present) alpha[code] = c;
+    if (c == 0) *sigma = total;
+}
+
+// ---- packed text: BITS in {2,4} bits per char (dense order-preserving codes),
+// 32/BITS chars per u32 word, char i at bit (i % CPW) * BITS.  BITS == 8 is the
+// raw byte text.  Small alphabets make the text L2-resident (100 MB DNA ->
+// 25 MB), which turns the random T[s-1] gathers of the induce into L2 hits.
+template <int BITS>
+__global__ void __launch_bounds__(BLK) k_pack(const uint8_t *__restrict__ text, uint64_t n,
+                                              const uint32_t *__restrict__ code_of, uint32_t *packed) {
+    constexpr int CPW = 32 / BITS;
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = (uint8_t)code_of[threadIdx.x];
+    __syncthreads();
+    uint64_t w = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+    uint64_t p0 = w * CPW;
+    if (p0 >= n) return;
+    uint32_t out = 0;
+    if (p0 + CPW <= n) {
+        if (CPW == 16) {
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + p0));
+            uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; j++) out |= (uint32_t)s_lut[(q[j >> 2] >> ((j & 3) * 8)) & 0xffu] << (j * BITS);
+        } else {
+            uint2 v = __ldg(reinterpret_cast<const uint2 *>(text + p0));
+            uint32_t q[2] = {v.x, v.y};
+#pragma unroll
+            for (int j = 0; j < 8; j++) out |= (uint32_t)s_lut[(q[j >> 2] >> ((j & 3) * 8)) & 0xffu] << (j * BITS);
+        }
+    } else {
+        for (int j = 0; j < CPW && p0 + j < n; j++) out |= (uint32_t)s_lut[__ldg(text + p0 + j)] << (j * BITS);
+    }
+    packed[w] = out;
+}
+
+template <int BITS>
+__device__ __forceinline__ uint32_t text_get(const void *__restrict__ base, uint32_t i) {
+    if (BITS == 8) return (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(base) + i);
+    constexpr int CPW = 32 / (BITS == 8 ? 4 : BITS);
+    return (__ldg(reinterpret_cast<const uint32_t *>(base) + i / CPW) >> ((i % CPW) * BITS)) & ((1u << BITS) - 1u);
+}
+
+// 32 bits of packed text starting at char position pos (BITS < 8): CPW chars,
+// char pos in the low bits.  Reads word w and w+1 (the packed buffer carries
+// one padding word).
+template <int BITS>
+__device__ __forceinline__ uint32_t text_bits(const void *__restrict__ base, uint32_t pos) {
+    constexpr int CPW = 32 / BITS;
+    const uint32_t *pk = reinterpret_cast<const uint32_t *>(base);
+    uint32_t w = pos / CPW, off = (pos % CPW) * BITS;
+    uint32_t lo = __ldg(pk + w), hi = __ldg(pk + w + 1);
+    return __funnelshift_r(lo, hi, off);
+}
+// Number of equal leading chars of text[a..) and text[b..), at most `limit`.
+template <int BITS>
+__device__ __forceinline__ uint32_t text_match(const void *__restrict__ base, uint32_t a, uint32_t b, uint32_t limit) {
+    uint32_t done = 0;
+    if (BITS == 8) {
+        const uint8_t *t = reinterpret_cast<const uint8_t *>(base);
+        while (done < limit && __ldg(t + a + done) == __ldg(t + b + done)) done++;
+        return done;
+    } else {
+        constexpr int CPW = 32 / (BITS == 8 ? 4 : BITS);
+        while (done < limit) {
+            uint32_t x = text_bits<(BITS == 8 ? 4 : BITS)>(base, a + done) ^ text_bits<(BITS == 8 ? 4 : BITS)>(base, b + done);
+            uint32_t take = limit - done < (uint32_t)CPW ? limit - done : (uint32_t)CPW;
+            uint32_t mask = take == (uint32_t)CPW ? 0xffffffffu : ((1u << (take * BITS)) - 1u);
+            x &= mask;
+            if (x) return done + (uint32_t)(__ffs(x) - 1) / BITS;
+            done += take;
+        }
+        return done;
+    }
+}
+// Distance from LMS position p to the next LMS position (> p), or 0 if none.
+__device__ __forceinline__ uint32_t next_lms_dist(const uint32_t *__restrict__ lmsb, uint32_t n, uint32_t p) {
+    uint32_t q = p + 1;
+    uint32_t nw = (n + 31) >> 5;
+    uint32_t w = q >> 5;
+    if (w >= nw) return 0;
+    uint32_t bits = __ldg(lmsb + w) >> (q & 31);
+    if (bits) return 1u + (uint32_t)(__ffs(bits) - 1);
+    uint32_t dist = 1u + (32u - (q & 31));
+    for (w = w + 1; w < nw; w++) {
+        bits = __ldg(lmsb + w);
+        if (bits) return dist + (uint32_t)(__ffs(bits) - 1);
+        dist += 32;
+    }
+    return 0;
 }
 
 // LMS positions in text order: lmspos[lmsrank[w] + k] = position of the k-th

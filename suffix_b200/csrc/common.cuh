@@ -266,16 +266,16 @@ namespace b200sa {
 constexpr unsigned long long OS_AGG = 1ull << 62, OS_INCL = 2ull << 62, OS_VAL = 0xffffffffull;
 constexpr int OS_MAX_PASSES = 8;
 
-template <class K>
-__global__ void __launch_bounds__(BLK) k_os_hist(const K *__restrict__ keys, uint64_t n, int npass, uint32_t *ghist) {
+template <class K, class KeyF>
+__global__ void __launch_bounds__(BLK) k_os_hist(KeyF keyf, uint64_t n, int npass, uint32_t shift0, uint32_t *ghist) {
     __shared__ uint32_t s_h[OS_MAX_PASSES][256];
     for (int p = 0; p < npass; p++) s_h[p][threadIdx.x] = 0;
     __syncthreads();
     for (uint64_t i0 = (uint64_t)blockIdx.x * BLK; i0 < n; i0 += (uint64_t)gridDim.x * BLK) {
         uint64_t i = i0 + threadIdx.x;
         bool valid = i < n;
-        K key = valid ? keys[i] : (K)0;
-        for (int p = 0; p < npass; p++) hist_add(s_h[p], (uint32_t)(key >> (8 * p)) & 0xffu, valid);
+        K key = valid ? keyf(i) : (K)0;
+        for (int p = 0; p < npass; p++) hist_add(s_h[p], (uint32_t)(key >> (shift0 + 8 * p)) & 0xffu, valid);
     }
     __syncthreads();
     for (int p = 0; p < npass; p++) {
@@ -292,8 +292,16 @@ __global__ void __launch_bounds__(BLK) k_os_scan(uint32_t *ghist) {
     ghist[blockIdx.x * 256 + threadIdx.x] = inc - v;
 }
 
+#ifndef OS_MINB
+#define OS_MINB 4
+#endif
 template <class K>
-__global__ void __launch_bounds__(BLK) k_os_pass(const K *__restrict__ kin, const uint32_t *__restrict__ vin, K *kout,
+struct LoadArr {
+    const K *a;
+    __device__ __forceinline__ K operator()(uint64_t i) const { return a[i]; }
+};
+template <class K, class KeyF, class ValF>
+__global__ void __launch_bounds__(BLK, OS_MINB) k_os_pass(KeyF keyf, ValF valf, K *kout,
                                                  uint32_t *vout, uint64_t n, uint32_t shift,
                                                  const uint32_t *__restrict__ gbase, volatile unsigned long long *status,
                                                  uint32_t *ticket) {
@@ -315,8 +323,8 @@ __global__ void __launch_bounds__(BLK) k_os_pass(const K *__restrict__ kin, cons
     for (int r = 0; r < ITEMS; r++) {
         uint64_t i = tb + (uint64_t)w * (ITEMS * 32) + r * 32 + l;
         bool valid = i < n;
-        key[r] = valid ? kin[i] : (K)0;
-        val[r] = valid ? vin[i] : 0u;
+        key[r] = valid ? keyf(i) : (K)0;
+        val[r] = valid ? valf(i) : 0u;
         d[r] = (uint32_t)(key[r] >> shift) & 0xffu;
         vm |= (valid ? 1u : 0u) << r;
     }

@@ -20,12 +20,15 @@
 #pragma once
 #include <cooperative_groups.h>
 #include "common.cuh"
+#include "classify.cuh"
 
 namespace b200sa {
 namespace cg = cooperative_groups;
 
 struct InduceArgs {
-    const uint8_t *text;     // level-0 text
+    const uint8_t *text;     // level-0 text (bytes)
+    const void *ptext;       // packed text (BITS 2/4) or the bytes themselves (BITS 8)
+    const uint32_t *alpha;   // code -> byte (BITS < 8)
     uint32_t n;
     uint32_t *sa;            // n slots
     uint8_t *pred;           // n bytes: T[s-1] of the entry in SA slot p (big steps only)
@@ -59,6 +62,7 @@ struct IndShared {
     uint32_t hist[256];
     uint32_t tcnt[256];
     uint32_t wcnt[NWARP][256];
+    uint32_t alpha[16];
     // broadcast area
     int32_t st_c, st_phase;
     uint32_t st_begin;
@@ -71,7 +75,7 @@ struct IndShared {
 enum { MODE_COUNT = 0, MODE_SCATTER = 1, MODE_SMALL = 2 };
 
 // Processes logical items [t0, t0+TILE) ∩ [0, g.len) of segment g.
-template <bool SPASS, int MODE>
+template <bool SPASS, int MODE, int BITS>
 __device__ __forceinline__ void induce_tile(const InduceArgs &A, IndShared &sh, const Seg &g, uint32_t t0) {
     const uint32_t w = warp_id(), l = lane_id();
     uint32_t s[ITEMS], d[ITEMS], rank[ITEMS], vm = 0;
@@ -93,7 +97,8 @@ __device__ __forceinline__ void induce_tile(const InduceArgs &A, IndShared &sh, 
         bool in = k < g.len;
         uint32_t p = g.rev ? g.base - k : g.base + k;
         if (MODE == MODE_SCATTER) d[r] = in ? (uint32_t)__ldcg(g.pred + p) : 0u;
-        else d[r] = (s[r] > 0) ? (uint32_t)__ldg(A.text + (s[r] - 1)) : 0u;
+        else if (BITS == 8) d[r] = (s[r] > 0) ? text_get<8>(A.ptext, s[r] - 1) : 0u;
+        else d[r] = (s[r] > 0) ? sh.alpha[text_get<BITS>(A.ptext, s[r] - 1)] : 0u;
         bool valid = in && s[r] > 0 && d[r] >= g.lo && d[r] <= g.hi;
         vm |= (valid ? 1u : 0u) << r;
         if (MODE == MODE_COUNT) {
@@ -163,7 +168,7 @@ __device__ void induce_peek(const InduceArgs &A, IndShared &sh) {
     sh.st_c = c; sh.st_phase = 0; sh.st_begin = 0;   // done
 }
 
-template <bool SPASS>
+template <bool SPASS, int BITS>
 __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
     __shared__ IndShared sh;
     cg::grid_group grid = cg::this_grid();
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
     sh.Lcnt[tid] = A.Lcnt[tid];
     if (SPASS) sh.S_or_lmsoff[tid] = A.Scnt[tid];
     else { sh.S_or_lmsoff[tid] = A.lms_off[tid]; if (tid == 0) sh.S_or_lmsoff[256] = A.lms_off[256]; }
+    if (BITS < 8 && tid < 16) sh.alpha[tid] = A.alpha[tid];
     uint32_t lastc = A.text[A.n - 1];
     sh.fill[tid] = (!SPASS && tid == lastc) ? 1u : 0u;
     if (tid == 0) { sh.st_c = SPASS ? 255 : 0; sh.st_phase = 0; sh.st_begin = 0; }
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
                     Seg g = sh.seg;
                     sh.base[tid] = sh.fill[tid];
                     __syncthreads();
-                    induce_tile<SPASS, MODE_SMALL>(A, sh, g, 0);
+                    induce_tile<SPASS, MODE_SMALL, BITS>(A, sh, g, 0);
                     sh.fill[tid] = sh.base[tid];
                     if (tid == 0) { sh.st_c = sh.ns_c; sh.st_phase = sh.ns_phase; sh.st_begin = sh.ns_begin; }
                     __syncthreads();
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
         // phase A: count + remember predecessors
         sh.hist[tid] = 0;
         __syncthreads();
-        for (uint32_t t = tb0; t < tb1; t++) induce_tile<SPASS, MODE_COUNT>(A, sh, g, t * TILE);
+        for (uint32_t t = tb0; t < tb1; t++) induce_tile<SPASS, MODE_COUNT, BITS>(A, sh, g, t * TILE);
         __syncthreads();
         if (bid < nact) cntbuf[(size_t)bid * 256u + tid] = sh.hist[tid];
         grid.sync();
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
             }
             sh.base[tid] = base;
             __syncthreads();
-            for (uint32_t t = tb0; t < tb1; t++) induce_tile<SPASS, MODE_SCATTER>(A, sh, g, t * TILE);
+            for (uint32_t t = tb0; t < tb1; t++) induce_tile<SPASS, MODE_SCATTER, BITS>(A, sh, g, t * TILE);
             __syncthreads();
             sh.fill[tid] += tot;
         }

@@ -51,27 +51,30 @@ struct MoveU32 {
 // LMS-substring equality with the reference's semantics (src/table.rs:802-820):
 // equal chars and equal type class position by position; equal once a later
 // position of either is a Valley; running off the text means different.
-__device__ __forceinline__ bool lms_substr_equal(const uint8_t *__restrict__ text, uint32_t n,
-                                                 const uint32_t *__restrict__ stype,
+// Two LMS substrings are equal iff they have the same length and the same
+// chars: the types of positions i..j-1 of a substring T[i..j] are determined by
+// its chars (T[j-1] > T[j] because j-1 is L and j is S), the first and last
+// positions are Valleys in both, and a length mismatch shows up in the
+// reference as a type mismatch at the shorter one's last position.  A substring
+// that runs off the text (no later Valley) equals nothing (:814-819).
+template <int BITS>
+__device__ __forceinline__ bool lms_substr_equal(const void *__restrict__ ptext, uint32_t n,
                                                  const uint32_t *__restrict__ lmsb, uint32_t a, uint32_t b) {
-    uint32_t i = a, j = b;
-    while (i < n && j < n) {
-        if (__ldg(text + i) != __ldg(text + j)) return false;
-        if (bit_at(stype, i) != bit_at(stype, j)) return false;
-        if (i > a && (bit_at(lmsb, i) || bit_at(lmsb, j))) return true;
-        i++; j++;
-    }
-    return false;
+    uint32_t la = next_lms_dist(lmsb, n, a);
+    if (la == 0) return false;
+    uint32_t lb = next_lms_dist(lmsb, n, b);
+    if (la != lb) return false;
+    return text_match<BITS>(ptext, a, b, la + 1) == la + 1;
 }
 // flag[i] = 1 iff sorted LMS substring i starts a new name
-__global__ void __launch_bounds__(BLK) k_name_flags(const uint8_t *__restrict__ text, uint32_t n,
-                                                    const uint32_t *__restrict__ stype,
+template <int BITS>
+__global__ void __launch_bounds__(BLK) k_name_flags(const void *__restrict__ ptext, uint32_t n,
                                                     const uint32_t *__restrict__ lmsb,
                                                     const uint32_t *__restrict__ sorted, uint32_t m, uint8_t *flag) {
     uint32_t i = blockIdx.x * BLK + threadIdx.x;
     if (i >= m) return;
     uint8_t f = 1;
-    if (i > 0) f = lms_substr_equal(text, n, stype, lmsb, sorted[i], sorted[i - 1]) ? 0 : 1;
+    if (i > 0) f = lms_substr_equal<BITS>(ptext, n, lmsb, sorted[i], sorted[i - 1]) ? 0 : 1;
     flag[i] = f;
 }
 struct InFlagU8 {
@@ -226,10 +229,24 @@ __global__ void __launch_bounds__(BLK) k_phi(const uint32_t *__restrict__ sa, ui
     uint32_t r = blockIdx.x * BLK + threadIdx.x;
     if (r < n) phi[sa[r]] = r ? sa[r - 1] : PHI_NONE;
 }
+// Binned variant: the (position, predecessor) pairs are first partitioned by the
+// top 8 bits of the position (one one-sweep pass), so that the scatter below
+// walks the phi array window by window and every 32-byte sector is completed in
+// L2 before it is written back (no read-modify-write of partial sectors).
+struct LoadPhiPrev {
+    const uint32_t *sa;
+    __device__ __forceinline__ uint32_t operator()(uint64_t r) const { return r ? sa[r - 1] : PHI_NONE; }
+};
+__global__ void __launch_bounds__(BLK) k_phi_apply(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ prev,
+                                                   uint32_t n, uint32_t *phi) {
+    uint32_t i = blockIdx.x * BLK + threadIdx.x;
+    if (i < n) phi[pos[i]] = prev[i];
+}
 // One thread owns LCP_CHUNK consecutive text positions: the first starts from
 // h = 0, the rest reuse h-1.  buf holds phi on entry and plcp on exit.
 constexpr int LCP_CHUNK = 32;
-__global__ void __launch_bounds__(BLK) k_plcp(const uint8_t *__restrict__ text, uint32_t n, uint32_t *buf) {
+template <int BITS>
+__global__ void __launch_bounds__(BLK) k_plcp(const void *__restrict__ ptext, uint32_t n, uint32_t *buf) {
     uint64_t t = (uint64_t)blockIdx.x * BLK + threadIdx.x;
     uint64_t i0 = t * LCP_CHUNK;
     if (i0 >= n) return;
@@ -239,9 +256,9 @@ __global__ void __launch_bounds__(BLK) k_plcp(const uint8_t *__restrict__ text, 
     for (uint64_t i = i0; i < i1; i++) {
         uint32_t j = buf[i];
         if (j == PHI_NONE) { buf[i] = 0; h = 0; continue; }
-        uint64_t a = i + h, b = (uint64_t)j + h;
-        while (a < n && b < n && __ldg(text + a) == __ldg(text + b)) { a++; b++; }
-        h = (uint32_t)(a - i);
+        uint32_t a = (uint32_t)i + h, b = j + h;     // a, b <= n (h never exceeds the shorter suffix)
+        uint32_t limit = n - (a > b ? a : b);
+        h += text_match<BITS>(ptext, a, b, limit);
         buf[i] = h;
         if (h > 0) h--;
     }
