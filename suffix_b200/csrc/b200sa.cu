@@ -597,8 +597,8 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
         CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
         CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
         uint32_t hb = tiles < 1184u ? tiles : 1184u;
-        LAUNCH(c, (k_os_hist<uint32_t, LoadArr<uint32_t>>), hb, LoadArr<uint32_t>{d_sa}, n, 1, shift, ghist);
-        LAUNCH(c, k_os_scan, 1u, ghist);
+        (void)hb;   // sa is a permutation: the digit bases are known without a histogram pass
+        LAUNCH(c, k_os_perm_base, 1u, ghist, shift, n32);
         LAUNCH(c, (k_os_pass<uint32_t, LoadArr<uint32_t>, LoadPhiPrev>), tiles, LoadArr<uint32_t>{d_sa}, LoadPhiPrev{d_sa},
                ptr<uint32_t>(c->phik), ptr<uint32_t>(c->phiv), n, shift, ghist,
                reinterpret_cast<volatile unsigned long long *>(c->os_status.p), ticket);

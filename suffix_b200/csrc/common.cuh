@@ -264,6 +264,16 @@ __global__ void __launch_bounds__(BLK) k_radix_scatter(DigF dig, MoveF mv, uint6
 namespace b200sa {
 
 constexpr unsigned long long OS_AGG = 1ull << 62, OS_INCL = 2ull << 62, OS_VAL = 0xffffffffull;
+// status words are self-contained (flag + count in one 64-bit word), so relaxed
+// gpu-scope accesses suffice; they avoid the system-scope LDG of `volatile`.
+__device__ __forceinline__ unsigned long long os_load(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void os_store(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
 constexpr int OS_MAX_PASSES = 8;
 
 template <class K, class KeyF>
@@ -284,6 +294,12 @@ __global__ void __launch_bounds__(BLK) k_os_hist(KeyF keyf, uint64_t n, int npas
     }
 }
 
+// digit bases when the keys are a permutation of 0..n-1 and the digit is their
+// top byte: bin d holds exactly the keys [d << shift, (d+1) << shift)
+__global__ void __launch_bounds__(BLK) k_os_perm_base(uint32_t *gbase, uint32_t shift, uint32_t n) {
+    uint64_t b = (uint64_t)threadIdx.x << shift;
+    gbase[threadIdx.x] = b < n ? (uint32_t)b : n;
+}
 // one block per pass: exclusive scan of its 256 digit totals, in place
 __global__ void __launch_bounds__(BLK) k_os_scan(uint32_t *ghist) {
     __shared__ uint32_t s_w[NWARP + 1];
@@ -335,17 +351,28 @@ __global__ void __launch_bounds__(BLK, OS_MINB) k_os_pass(KeyF keyf, ValF valf, 
         uint32_t inc = block_incl_scan<OpSum>(cnt, s_w, &total);
         uint32_t texcl = inc - cnt;
         s_texcl[dg] = texcl;
-        volatile unsigned long long *mine = status + (uint64_t)tile * 256 + dg;
-        *mine = OS_AGG | cnt;
+        unsigned long long *mine = const_cast<unsigned long long *>(status) + (uint64_t)tile * 256 + dg;
+        os_store(mine, OS_AGG | cnt);
         uint32_t excl = 0;
-        for (uint32_t t = tile; t-- > 0;) {
-            volatile unsigned long long *q = status + (uint64_t)t * 256 + dg;
-            unsigned long long v;
-            do { v = *q; } while ((v >> 62) == 0);
-            excl += (uint32_t)(v & OS_VAL);
-            if ((v >> 62) == 2) break;
+        // look back over predecessor tiles, four status words in flight at a time
+        int64_t t = (int64_t)tile - 1;
+        bool done = false;
+        while (t >= 0 && !done) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                v[k] = (t - k >= 0) ? os_load(const_cast<unsigned long long *>(status) + (uint64_t)(t - k) * 256 + dg) : OS_INCL;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (done || t - k < 0) break;
+                unsigned long long x = v[k];
+                while ((x >> 62) == 0) x = os_load(const_cast<unsigned long long *>(status) + (uint64_t)(t - k) * 256 + dg);
+                excl += (uint32_t)(x & OS_VAL);
+                if ((x >> 62) == 2) done = true;
+            }
+            t -= 4;
         }
-        *mine = OS_INCL | (unsigned long long)(excl + cnt);
+        os_store(mine, OS_INCL | (unsigned long long)(excl + cnt));
         s_gb[dg] = gbase[dg] + excl - texcl;
     }
     __syncthreads();
