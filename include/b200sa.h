@@ -81,6 +81,31 @@ int b200sa_positions_dev(b200sa_ctx *ctx, const uint8_t *d_text, uint64_t n,
                          const uint64_t *d_q_off, uint32_t nq,
                          uint32_t *d_start, uint32_t *d_end, void *stream);
 
+/* ---- multi-GPU shards (BASELINE config 5) ----
+ * Type classification + LMS flags + (byte,type) histogram of ONE contiguous
+ * shard text[lo,hi) of a longer text, one shard per GPU/process; the caller
+ * (suffix_b200/sharded.py, torch.distributed over NCCL) exchanges the tiny
+ * summaries between the two calls.  Replaces SuffixTypes::compute
+ * (src/table.rs:592-615) and Bins::find_sizes (:686-704) for sharded input.
+ *
+ * 1. b200sa_shard_summary: *state_out = type of the shard's FIRST position as
+ *    far as the shard (plus next_char = T[hi], or -1 at the end of the text)
+ *    determines it: 0 Descending(L), 1 Ascending(S), 2 undetermined (every
+ *    char up to and including next_char is equal).
+ * 2. all-gather the states; tail_carry of shard r = first state != 2 among the
+ *    shards after r.
+ * 3. b200sa_shard_classify with prev_char = T[lo-1] (-1 for the first shard),
+ *    next_char, tail_carry: S-type and LMS bitmaps (bit i&31 of word i>>5,
+ *    shard-local positions), shard-local LMS positions (ascending), the
+ *    768-bin histogram [0,256) L, [256,512) S-non-LMS, [512,768) LMS (host,
+ *    u64, to be all-reduced) and the number of LMS positions.
+ * d_shard must be 16-byte aligned. */
+int b200sa_shard_summary(b200sa_ctx *ctx, const uint8_t *d_shard, uint64_t len, int next_char,
+                         int *state_out, void *stream);
+int b200sa_shard_classify(b200sa_ctx *ctx, const uint8_t *d_shard, uint64_t len, int prev_char, int next_char,
+                          int tail_carry, uint32_t *d_stype_words, uint32_t *d_lms_words,
+                          uint32_t *d_lmspos, uint64_t cap_lms, uint64_t *hist768, uint64_t *m_out, void *stream);
+
 /* ---- introspection (bench / tests) ---- */
 
 typedef struct {

@@ -44,6 +44,8 @@ def lib():
         "b200sa_build_dev": ([vp, vp, u64, vp, vp], ci),
         "b200sa_lcp_dev": ([vp, vp, u64, vp, vp, vp], ci),
         "b200sa_positions_dev": ([vp, vp, u64, vp, vp, vp, u32, vp, vp, vp], ci),
+        "b200sa_shard_summary": ([vp, vp, u64, ci, ctypes.POINTER(ci), vp], ci),
+        "b200sa_shard_classify": ([vp, vp, u64, ci, ci, ci, vp, vp, vp, u64, vp, ctypes.POINTER(u64), vp], ci),
         "b200sa_last_stats": ([vp, ctypes.POINTER(Stats)], ci),
         "b200sa_set_timing": ([vp, ci], ci),
         "b200sa_last_phase_times": ([vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ci], ci),
@@ -123,6 +125,21 @@ class Context:
 
     def positions_dev(self, d_text, n, d_sa, d_q, d_qoff, nq, d_start, d_end, stream: int = 0):
         self._check(lib().b200sa_positions_dev(self._h, d_text, n, d_sa, d_q, d_qoff, nq, d_start, d_end, stream))
+
+    # ---- multi-GPU shards
+    def shard_summary(self, d_shard: int, length: int, next_char: int, stream: int = 0) -> int:
+        st = ctypes.c_int(0)
+        self._check(lib().b200sa_shard_summary(self._h, d_shard, length, next_char, ctypes.byref(st), stream))
+        return int(st.value)
+
+    def shard_classify(self, d_shard: int, length: int, prev_char: int, next_char: int, tail_carry: int,
+                       d_stype: int = 0, d_lms: int = 0, d_lmspos: int = 0, cap_lms: int = 0, stream: int = 0):
+        hist = np.zeros(768, dtype=np.uint64)
+        m = ctypes.c_uint64(0)
+        self._check(lib().b200sa_shard_classify(self._h, d_shard, length, prev_char, next_char, tail_carry,
+                                                d_stype, d_lms, d_lmspos, cap_lms, hist.ctypes.data,
+                                                ctypes.byref(m), stream))
+        return hist, int(m.value)
 
     # ---- introspection
     def set_timing(self, on: bool):

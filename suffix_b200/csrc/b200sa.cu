@@ -399,7 +399,8 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
 }
 
 // ------------------------------------------------------- the level driver
-static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *m_out) {
+static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *m_out,
+                        ShardEdge edge = ShardEdge{-1, -1, ST_L}) {
     uint64_t nw = (n + 31) / 32;
     uint32_t nbc = cdiv(nw, CLS_WORDS);
     TRY(ensure(c, c->stype, nw * 4));
@@ -414,9 +415,9 @@ static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t
     uint32_t *sm = ptr<uint32_t>(c->small);
     CU_TRY(c, cudaMemsetAsync(hist, 0, 768 * 4, c->stream));
     CU_TRY(c, cudaMemsetAsync(sm, 0, 4096, c->stream));
-    LAUNCH(c, k_cls_block_state, nbc, text, n, ptr<uint8_t>(c->blkstate));
-    LAUNCH(c, k_cls_carry, 1, ptr<uint8_t>(c->blkstate), nbc, ptr<uint8_t>(c->carry));
-    LAUNCH(c, k_cls_types, nbc, text, n, ptr<uint8_t>(c->carry), ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb), hist);
+    LAUNCH(c, k_cls_block_state, nbc, text, n, ptr<uint8_t>(c->blkstate), edge);
+    LAUNCH(c, k_cls_carry, 1, ptr<uint8_t>(c->blkstate), nbc, ptr<uint8_t>(c->carry), edge.next_char >= 0 ? edge.tail_carry : ST_L);
+    LAUNCH(c, k_cls_types, nbc, text, n, ptr<uint8_t>(c->carry), ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb), hist, edge);
     LAUNCH(c, k_bucket_tables, 1, hist, tab + T_BSTART, tab + T_LCNT, tab + T_SCNT, tab + T_LMSOFF, tab + T_CODE,
            tab + T_ALPHA, sm + 3);
     CU_TRY(c, cudaGetLastError());
@@ -820,6 +821,59 @@ int b200sa_positions_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const
         LAUNCH(c, k_positions, cdiv(nq, BLK), d_text, (uint32_t)n, d_sa, d_queries, d_q_off, nq, d_start, d_end);
         CU_TRY(c, cudaGetLastError());
     }
+    return end_call(c);
+}
+
+// ------------------------------------------------------------ multi-GPU shards
+int b200sa_shard_summary(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, int next_char, int *state_out, void *stream) {
+    if (!c || !d_shard || len < 1 || len > 0xFFFFFFFFull || !state_out || next_char > 255) return B200SA_ERR_BAD_ARG;
+    if (((uintptr_t)d_shard & 15) != 0) { c->last_error = "shard pointer must be 16-byte aligned"; return B200SA_ERR_BAD_ARG; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    uint64_t nw = (len + 31) / 32;
+    uint32_t nbc = cdiv(nw, CLS_WORDS);
+    TRY(ensure(c, c->blkstate, nbc));
+    TRY(ensure(c, c->carry, nbc));
+    TRY(ensure(c, c->small, 4096));
+    ShardEdge edge{next_char, -1, ST_P};
+    LAUNCH(c, k_cls_block_state, nbc, d_shard, len, ptr<uint8_t>(c->blkstate), edge);
+    LAUNCH(c, k_cls_carry, 1, ptr<uint8_t>(c->blkstate), nbc, ptr<uint8_t>(c->carry), (uint32_t)ST_P);
+    CU_TRY(c, cudaGetLastError());
+    uint8_t h[2];
+    CU_TRY(c, cudaMemcpyAsync(&h[0], c->blkstate.p, 1, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(&h[1], c->carry.p, 1, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    *state_out = (h[0] != ST_P) ? h[0] : h[1];
+    return end_call(c);
+}
+
+int b200sa_shard_classify(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, int prev_char, int next_char,
+                          int tail_carry, uint32_t *d_stype_words, uint32_t *d_lms_words, uint32_t *d_lmspos,
+                          uint64_t cap_lms, uint64_t *hist768, uint64_t *m_out, void *stream) {
+    if (!c || !d_shard || len < 1 || len > 0xFFFFFFFFull || prev_char > 255 || next_char > 255) return B200SA_ERR_BAD_ARG;
+    if (next_char >= 0 && tail_carry != (int)ST_L && tail_carry != (int)ST_S) return B200SA_ERR_BAD_ARG;
+    if (((uintptr_t)d_shard & 15) != 0) { c->last_error = "shard pointer must be 16-byte aligned"; return B200SA_ERR_BAD_ARG; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    uint32_t m = 0;
+    ShardEdge edge{next_char, prev_char, next_char >= 0 ? (uint32_t)tail_carry : ST_L};
+    TRY(classify_dev(c, d_shard, len, &m, edge));
+    uint64_t nw = (len + 31) / 32;
+    if (d_stype_words) CU_TRY(c, cudaMemcpyAsync(d_stype_words, c->stype.p, nw * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_lms_words) CU_TRY(c, cudaMemcpyAsync(d_lms_words, c->lmsb.p, nw * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (d_lmspos && m > 0) {
+        uint64_t k = m < cap_lms ? m : cap_lms;
+        CU_TRY(c, cudaMemcpyAsync(d_lmspos, c->lmspos.p, k * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (hist768) {
+        uint32_t h32[768];
+        CU_TRY(c, cudaMemcpyAsync(h32, ptr<uint32_t>(c->tables) + T_HIST, sizeof h32, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 768; i++) hist768[i] = h32[i];
+    } else {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    if (m_out) *m_out = m;
     return end_call(c);
 }
 

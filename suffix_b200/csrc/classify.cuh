@@ -20,10 +20,20 @@ constexpr uint32_t ST_L = 0, ST_S = 1, ST_P = 2;
 constexpr int CLS_WORDS = BLK;             // words per block
 constexpr int CLS_BYTES = CLS_WORDS * 32;  // 8192 text bytes per block
 
+// A shard of a longer text (multi-GPU row): the chars just outside
+// the shard and the resolved type of the first position after it.  For a whole
+// text: next_char = prev_char = -1.
+struct ShardEdge {
+    int32_t next_char;    // T[hi] or -1 when the shard ends the text
+    int32_t prev_char;    // T[lo-1] or -1 when the shard starts the text
+    uint32_t tail_carry;  // type of position hi (ST_L / ST_S / ST_P = unknown); only read when next_char >= 0
+};
+
 // Loads the 32 bytes of word w (zero beyond n) plus the following byte.
 // Returns the number of valid positions in the word.
 __device__ __forceinline__ uint32_t load_word(const uint8_t *__restrict__ text, uint64_t n, uint64_t w,
-                                              uint32_t (&c)[8], uint32_t &nextc, bool &has_next) {
+                                              uint32_t (&c)[8], uint32_t &nextc, bool &has_next,
+                                              const ShardEdge &edge) {
     uint64_t p0 = w * 32;
     uint32_t cnt;
     if (p0 + 32 <= n) {
@@ -42,6 +52,11 @@ __device__ __forceinline__ uint32_t load_word(const uint8_t *__restrict__ text, 
     }
     has_next = (p0 + 32 < n);
     nextc = has_next ? (uint32_t)__ldg(text + p0 + 32) : 0u;
+    if (!has_next && cnt > 0 && edge.next_char >= 0) {     // the shard continues in the next shard
+        has_next = true;
+        if (cnt == 32) nextc = (uint32_t)edge.next_char;
+        else c[cnt >> 2] |= (uint32_t)edge.next_char << ((cnt & 3) * 8);
+    }
     return cnt;
 }
 
@@ -87,12 +102,12 @@ __device__ __forceinline__ uint32_t first_nonp_right(uint32_t mine, uint32_t *s_
 
 // Pass A: block state = first non-EQ rel in the block's byte range.
 __global__ void __launch_bounds__(BLK) k_cls_block_state(const uint8_t *__restrict__ text, uint64_t n,
-                                                         uint8_t *blk_state) {
+                                                         uint8_t *blk_state, ShardEdge edge) {
     __shared__ uint32_t s_warp[NWARP];
     uint64_t w = (uint64_t)blockIdx.x * CLS_WORDS + threadIdx.x;
     uint32_t c[8], nextc, lt, gt;
     bool has_next;
-    uint32_t cnt = load_word(text, n, w, c, nextc, has_next);
+    uint32_t cnt = load_word(text, n, w, c, nextc, has_next, edge);
     word_rel(c, cnt, nextc, has_next, lt, gt);
     uint32_t ne = lt | gt;
     uint32_t mine = ne ? ((lt >> (__ffs(ne) - 1)) & 1u) : ST_P;
@@ -102,9 +117,10 @@ __global__ void __launch_bounds__(BLK) k_cls_block_state(const uint8_t *__restri
 
 // Pass B (single block): carry_in[b] = first non-P state among blocks > b.
 // Walks chunks of 256 block states from the right with a running carry.
-__global__ void __launch_bounds__(BLK) k_cls_carry(const uint8_t *blk_state, uint32_t nb, uint8_t *carry_in) {
+__global__ void __launch_bounds__(BLK) k_cls_carry(const uint8_t *blk_state, uint32_t nb, uint8_t *carry_in,
+                                                   uint32_t tail_carry) {
     __shared__ uint32_t s_warp[NWARP];
-    uint32_t carry = ST_L;     // beyond the last block: unused (position n-1 is never EQ)
+    uint32_t carry = tail_carry;   // whole text: unused (position n-1 is never EQ); shard: type of position hi
     uint32_t nchunks = (nb + BLK - 1) / BLK;
     for (uint32_t ch = nchunks; ch-- > 0;) {
         uint32_t b = ch * BLK + threadIdx.x;
@@ -124,7 +140,7 @@ __global__ void __launch_bounds__(BLK) k_cls_carry(const uint8_t *blk_state, uin
 // non-LMS counts, [512,768) LMS counts, per byte value.
 __global__ void __launch_bounds__(BLK) k_cls_types(const uint8_t *__restrict__ text, uint64_t n,
                                                    const uint8_t *carry_in, uint32_t *stype, uint32_t *lmsb,
-                                                   uint32_t *hist768) {
+                                                   uint32_t *hist768, ShardEdge edge) {
     __shared__ uint32_t s_warp[NWARP];
     __shared__ uint32_t s_sw[BLK];
     __shared__ uint32_t s_hist[768];
@@ -133,7 +149,7 @@ __global__ void __launch_bounds__(BLK) k_cls_types(const uint8_t *__restrict__ t
     uint64_t nw = (n + 31) / 32;
     uint32_t c[8], nextc, lt, gt;
     bool has_next;
-    uint32_t cnt = load_word(text, n, w, c, nextc, has_next);
+    uint32_t cnt = load_word(text, n, w, c, nextc, has_next, edge);
     word_rel(c, cnt, nextc, has_next, lt, gt);
     uint32_t ne = lt | gt;
     uint32_t mine = ne ? ((lt >> (__ffs(ne) - 1)) & 1u) : ST_P;
@@ -153,7 +169,11 @@ __global__ void __launch_bounds__(BLK) k_cls_types(const uint8_t *__restrict__ t
     // type bit of the position just before this word
     uint32_t pb;
     if (threadIdx.x > 0) pb = s_sw[threadIdx.x - 1] >> 31;
-    else if (w == 0) pb = 1u;                      // position 0 is never a Valley (src/table.rs:465)
+    else if (w == 0 && edge.prev_char < 0) pb = 1u;  // position 0 is never a Valley (src/table.rs:465)
+    else if (w == 0) {                               // shard start: type of position lo-1 from the halo char
+        uint32_t c1 = (uint32_t)edge.prev_char, c2 = byte_of(c, 0);
+        pb = (c1 < c2) ? 1u : (c1 > c2) ? 0u : (sw & 1u);
+    }
     else if (cnt == 0) pb = 0u;
     else {
         uint32_t c1 = __ldg(text + w * 32 - 1), c2 = byte_of(c, 0);

@@ -1,0 +1,161 @@
+"""Sharded classification: host coordination under gloo with a numpy
+engine (CPU, world_size 2 and 3) and the CUDA kernels' halo logic on one GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle
+from suffix_b200 import gen, sharded
+from tests import families
+from tests.shard_ref import NumpyShardEngine
+
+
+def _expected(t):
+    ty = oracle.types(t)
+    S = (ty != 1).astype(np.uint8)
+    lms = (ty == 2).astype(np.uint8)
+    hist = np.zeros(768, dtype=np.uint64)
+    np.add.at(hist, t.astype(np.int64) + 256 * np.array([1, 0, 2])[ty], 1)
+    return S, lms, hist
+
+
+def _unpack(words, n):
+    return np.unpackbits(np.asarray(words).view(np.uint8), bitorder="little")[:n]
+
+
+def _cuts(n, parts, rng):
+    c = sorted(rng.choice(np.arange(1, n), size=parts - 1, replace=False).tolist()) if n > parts else list(range(1, parts))
+    return [0] + c + [n]
+
+
+def _worker(rank, world, port, texts, cutsets, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = NumpyShardEngine()
+    out = []
+    for t, cuts in zip(texts, cutsets):
+        shard = t[cuts[rank]:cuts[rank + 1]]
+        r = sharded.classify_sharded(eng, shard, dist=dist)
+        out.append((r.lo, np.asarray(r.stype_words), np.asarray(r.lms_words), np.asarray(r.lmspos_local),
+                    r.m_offset, r.m_total, r.hist_global, len(shard)))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_gloo(world):
+    rng = np.random.default_rng(5 + world)
+    texts = [np.frombuffer(d, dtype=np.uint8) for _, d in families.adversarial() if len(d) >= 8][:18]
+    texts += [gen.dna(50_000), np.full(5000, 65, dtype=np.uint8),
+              np.concatenate([np.full(3000, 66, dtype=np.uint8), np.full(3000, 65, dtype=np.uint8)])]
+    cutsets = [_cuts(len(t), world, rng) for t in texts]
+    cutsets[-2] = [0] + [len(texts[-2]) * k // world for k in range(1, world)] + [len(texts[-2])]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, texts, cutsets, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    for k, t in enumerate(texts):
+        S, lms, hist = _expected(t)
+        pos_all = []
+        for r in range(world):
+            lo, sw, lw, pos, moff, mtot, hg, n_loc = res[r][k]
+            assert lo == cutsets[k][r]
+            assert np.array_equal(_unpack(sw, n_loc), S[lo:lo + n_loc]), (k, r)
+            assert np.array_equal(_unpack(lw, n_loc), lms[lo:lo + n_loc]), (k, r)
+            assert np.array_equal(hg, hist)
+            assert moff == len(pos_all) and mtot == int(lms.sum())
+            pos_all += (pos.astype(np.int64) + lo).tolist()
+        assert pos_all == np.flatnonzero(lms).tolist()
+
+
+@pytest.mark.gpu
+def test_sharded_cuda_kernels_single_gpu():
+    """The CUDA shard kernels with halos, shards processed one after another on
+    one GPU (same code path a rank runs; the collectives are covered above)."""
+    from suffix_b200 import _lib
+    ctx = _lib.Context(0)
+    eng = sharded.CudaShardEngine(ctx, torch)
+    rng = np.random.default_rng(11)
+    texts = [np.frombuffer(d, dtype=np.uint8) for _, d in families.adversarial() if len(d) >= 64]
+    texts += [gen.dna(3_000_017), gen.rand_bytes(1_000_003), np.full(100_000, 65, dtype=np.uint8)]
+    for t in texts:
+        S, lms, hist = _expected(t)
+        n = len(t)
+        parts = 3
+        cuts = [0] + sorted((rng.integers(1, n // 16, parts - 1) * 16 % n).tolist()) + [n]   # 16-byte aligned cuts
+        cuts = sorted(set(cuts))
+        d_t = torch.from_numpy(t.copy()).cuda()
+        shards = [d_t[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
+        edges = [eng.edge_bytes(s) for s in shards]
+        states = [eng.summary(s, edges[i + 1][0] if i + 1 < len(shards) else -1) for i, s in enumerate(shards)]
+        tails = sharded.resolve_tail_carries(states)
+        hsum = np.zeros(768, dtype=np.uint64)
+        pos_all = []
+        for i, s in enumerate(shards):
+            nxt = edges[i + 1][0] if i + 1 < len(shards) else -1
+            prv = edges[i - 1][1] if i > 0 else -1
+            sw, lw, pos, h, m = eng.classify(s, prv, nxt, tails[i])
+            lo, n_loc = cuts[i], s.numel()
+            assert np.array_equal(_unpack(sw.cpu().numpy(), n_loc), S[lo:lo + n_loc])
+            assert np.array_equal(_unpack(lw.cpu().numpy(), n_loc), lms[lo:lo + n_loc])
+            hsum += h
+            pos_all += (pos.cpu().numpy().view(np.uint32).astype(np.int64) + lo).tolist()
+        assert np.array_equal(hsum, hist)
+        assert pos_all == np.flatnonzero(lms).tolist()
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from suffix_b200 import _lib
+    ctx = _lib.Context(rank)
+    eng = sharded.CudaShardEngine(ctx, torch)
+    n = 8_000_000
+    t = gen.dna(n * world)                         # every rank generates the same text, keeps its shard
+    shard = torch.from_numpy(t[rank * n:(rank + 1) * n].copy()).cuda()
+    r = sharded.classify_sharded(eng, shard, dist=dist, device=torch.device("cuda", rank))
+    S, lms, hist = _expected(t)
+    ok = np.array_equal(_unpack(r.stype_words.cpu().numpy(), n), S[r.lo:r.lo + n]) and \
+        np.array_equal(_unpack(r.lms_words.cpu().numpy(), n), lms[r.lo:r.lo + n]) and \
+        np.array_equal(r.hist_global, hist) and r.m_total == int(lms.sum())
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_nccl_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}
