@@ -55,7 +55,7 @@ struct b200sa_ctx {
     DevBuf text, sa, lcp;                      // staging for the host API
     DevBuf pred, stype, lmsb, lmsrank, lmspos, lmslist, lmspred, sorted, flag, reduced, sa_r;
     DevBuf blkstate, carry, tables, small, scan_partial, radix_cnt, blkcnt;
-    DevBuf os_hist, os_status, phik, phiv;
+    DevBuf os_hist, os_status, phik, phiv, runscr;
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
     DevBuf packed;
     int bits = 8;                    // bits per char of the packed text of the current call (2, 4 or 8 = raw)
@@ -392,6 +392,7 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
     A.blk_cnt = ptr<uint32_t>(c->blkcnt);
     uint32_t *sm = ptr<uint32_t>(c->small);
     A.g_fill = sm + 64; A.g_state = reinterpret_cast<int32_t *>(sm + 320); A.err = sm + 32;
+    A.run_scratch = ptr<uint32_t>(c->runscr);
     void *args[] = {&A};
     CU_TRY(c, cudaLaunchCooperativeKernel(induce_fn(spass, c->bits), dim3(c->cur_induce_blocks), dim3(BLK), args, 0, c->stream));
     c->launches++;
@@ -466,6 +467,7 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     TRY(ensure(c, c->lmslist, (size_t)m * 4));
     TRY(ensure(c, c->lmspred, m));
     TRY(ensure(c, c->blkcnt, (size_t)2 * c->induce_blocks * 256 * 4));
+    TRY(ensure(c, c->runscr, (size_t)TILE * 4));
     uint32_t *lmslist = ptr<uint32_t>(c->lmslist);
     if (m > 0) {
         TRY(ensure(c, c->sorted, (size_t)m * 4));
@@ -705,7 +707,7 @@ void b200sa_ctx_destroy(b200sa_ctx *c) {
     DevBuf *bufs[] = {&c->text, &c->sa, &c->lcp, &c->pred, &c->stype, &c->lmsb, &c->lmsrank, &c->lmspos, &c->lmslist,
                       &c->lmspred, &c->sorted, &c->flag, &c->reduced, &c->sa_r, &c->blkstate, &c->carry, &c->tables,
                       &c->small, &c->scan_partial, &c->radix_cnt, &c->blkcnt, &c->k32b, &c->k64a, &c->k64b, &c->v0,
-                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv};
+                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);

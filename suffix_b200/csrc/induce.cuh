@@ -42,6 +42,7 @@ struct InduceArgs {
     uint32_t *g_fill;        // [256] hand-off after small episodes
     int32_t *g_state;        // [4]   hand-off: c, phase, begin
     uint32_t *err;           // [4]   err[0] != 0 => invariant violated
+    uint32_t *run_scratch;   // [TILE] run-skipping: terminal entries in scan order
 };
 
 struct Seg {
@@ -63,6 +64,15 @@ struct IndShared {
     uint32_t tcnt[256];
     uint32_t wcnt[NWARP][256];
     uint32_t alpha[16];
+    // run skipping (block 0, small episodes)
+    uint32_t ent[TILE];      // entries of the current chain list
+    uint32_t rl[TILE];       // their run lengths to the left
+    uint32_t alive[TILE];    // entries still alive in the current epoch, in list order
+    uint32_t sw[NWARP + 1];
+    uint32_t red;
+    uint32_t streak;
+    int32_t streak_c;
+    int32_t is_chain;
     // broadcast area
     int32_t st_c, st_phase;
     uint32_t st_begin;
@@ -128,6 +138,7 @@ __device__ void induce_peek(const InduceArgs &A, IndShared &sh) {
     int32_t c = sh.st_c, phase = sh.st_phase;
     uint32_t begin = sh.st_begin;
     sh.has = 0;
+    sh.is_chain = 0;
     while (SPASS ? (c >= 0) : (c <= 255)) {
         if (phase == 0) {
             uint32_t end = sh.fill[c];
@@ -135,7 +146,7 @@ __device__ void induce_peek(const InduceArgs &A, IndShared &sh) {
                 sh.seg.src = A.sa; sh.seg.pred = A.pred; sh.seg.len = end - begin;
                 if (SPASS) { sh.seg.base = sh.bstart[c + 1] - 1u - begin; sh.seg.lo = 0; sh.seg.hi = (uint32_t)c; sh.seg.rev = 1; }
                 else       { sh.seg.base = sh.bstart[c] + begin; sh.seg.lo = (uint32_t)c; sh.seg.hi = 255; sh.seg.rev = 0; }
-                sh.ns_c = c; sh.ns_phase = 0; sh.ns_begin = end; sh.has = 1;
+                sh.ns_c = c; sh.ns_phase = 0; sh.ns_begin = end; sh.has = 1; sh.is_chain = 1;
                 return;
             }
             // chain exhausted: the part must be complete (reference invariant)
@@ -168,6 +179,157 @@ __device__ void induce_peek(const InduceArgs &A, IndShared &sh) {
     sh.st_c = c; sh.st_phase = 0; sh.st_begin = 0;   // done
 }
 
+// ---------------------------------------------------------------- run skipping
+// A chain inside bucket c advances one position per round along a run of the
+// byte c, so a run of length 10^7 (poly-N in a genome, zero padding) would cost
+// 10^7 rounds.  Once a bucket has needed RUN_STREAK consecutive small chain
+// rounds, block 0 finishes the whole chain of the bucket at once: with l_j the
+// length of the run of c to the left of entry e_j of the current list, round r
+// emits {e_j - r : l_j >= r} in list order.  Rounds between two consecutive
+// distinct l values share one alive set ("epoch"), so each epoch is one block
+// scan plus a fully parallel emission.  The entries that end their run
+// ("terminals", e_j - l_j, in (l_j, j) order = their order in SA) are then
+// pushed through one ordinary small step for the other buckets.
+constexpr uint32_t RUN_STREAK = 8;
+constexpr uint32_t RUN_LOCAL = 64;          // per-thread probe before the cooperative scan
+constexpr uint32_t RUN_INF = 0xffffffffu;
+
+// number of consecutive bytes == c at positions start, start-1, ... (block-cooperative)
+__device__ __noinline__ uint32_t run_left_coop(const uint8_t *__restrict__ text, uint32_t start, uint32_t c, IndShared &sh) {
+    uint32_t count = 0;
+    int64_t cur = start;
+    while (true) {
+        if (threadIdx.x == 0) sh.red = RUN_INF;
+        __syncthreads();
+        uint32_t first = RUN_INF;
+        for (int q = 0; q < 16; q++) {
+            int64_t pos = cur - ((int64_t)threadIdx.x * 16 + q);
+            bool same = pos >= 0 && (uint32_t)__ldg(text + pos) == c;
+            if (!same) { first = threadIdx.x * 16 + q; break; }
+        }
+        if (first != RUN_INF) atomicMin(&sh.red, first);
+        __syncthreads();
+        uint32_t m = sh.red;
+        __syncthreads();
+        if (m != RUN_INF) return count + m;
+        count += 4096;
+        cur -= 4096;
+    }
+}
+
+template <bool SPASS, int BITS>
+__device__ __noinline__ void induce_run_skip(const InduceArgs &A, IndShared &sh, const Seg &g, uint32_t c) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t k = g.len;                       // <= TILE; thread t owns list items [8t, 8t+8)
+    // ---- entries and locally probed run lengths
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        uint32_t j = tid * ITEMS + i;
+        uint32_t e = 0, r = 0;
+        if (j < k) {
+            uint32_t p = g.rev ? g.base - j : g.base + j;
+            e = __ldcg(g.src + p);
+            while (r < RUN_LOCAL && e > r && (uint32_t)__ldg(A.text + (e - 1 - r)) == c) r++;
+            if (r == RUN_LOCAL) r = RUN_INF;        // long: resolved cooperatively below
+        }
+        sh.ent[j] = e;
+        sh.rl[j] = r;
+    }
+    __syncthreads();
+    for (uint32_t j = 0; j < k; j++) {
+        if (sh.rl[j] == RUN_INF) {                  // uniform across the block
+            uint32_t e = sh.ent[j];
+            uint32_t more = (e > RUN_LOCAL) ? run_left_coop(A.text, e - 1 - RUN_LOCAL, c, sh) : 0u;
+            __syncthreads();
+            if (tid == 0) sh.rl[j] = RUN_LOCAL + more;
+            __syncthreads();
+        }
+    }
+    const uint32_t F = sh.fill[c];
+    uint64_t O = 0;                                 // chain entries emitted so far
+    uint32_t tcount = 0;                            // terminals emitted so far
+    uint32_t t_prev = 0;
+    bool first_epoch = true;                        // epoch 0 only collects the terminals with l == 0
+    while (true) {
+        // threshold of this epoch: smallest run length > t_prev (or, first, exactly 0)
+        uint32_t thr;
+        if (first_epoch) thr = 0;
+        else {
+            uint32_t mine = RUN_INF;
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                uint32_t j = tid * ITEMS + i;
+                if (j < k && sh.rl[j] > t_prev && sh.rl[j] < mine) mine = sh.rl[j];
+            }
+            if (tid == 0) sh.red = RUN_INF;
+            __syncthreads();
+            if (mine != RUN_INF) atomicMin(&sh.red, mine);
+            __syncthreads();
+            thr = sh.red;
+            __syncthreads();
+            if (thr == RUN_INF) break;
+            // alive set of rounds t_prev+1 .. thr: run length >= thr
+            uint32_t own = 0;
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                uint32_t j = tid * ITEMS + i;
+                if (j < k && sh.rl[j] >= thr) own++;
+            }
+            uint32_t a;
+            uint32_t inc = block_incl_scan<OpSum>(own, sh.sw, &a);
+            uint32_t at = inc - own;
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                uint32_t j = tid * ITEMS + i;
+                if (j < k && sh.rl[j] >= thr) sh.alive[at++] = sh.ent[j];
+            }
+            __syncthreads();
+            uint64_t items = (uint64_t)(thr - t_prev) * a;
+            for (uint64_t idx = tid; idx < items; idx += BLK) {
+                uint32_t r_off = (uint32_t)(idx / a), jj = (uint32_t)(idx % a);
+                uint32_t pos = F + (uint32_t)(O + idx);
+                uint32_t slot = SPASS ? (sh.bstart[c + 1] - 1u - pos) : (sh.bstart[c] + pos);
+                A.sa[slot] = sh.alive[jj] - (t_prev + 1u + r_off);
+            }
+            O += items;
+        }
+        // terminals of this epoch: run length == thr, in list order
+        {
+            uint32_t own = 0;
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                uint32_t j = tid * ITEMS + i;
+                if (j < k && sh.rl[j] == thr) own++;
+            }
+            uint32_t tot;
+            uint32_t inc = block_incl_scan<OpSum>(own, sh.sw, &tot);
+            uint32_t at = tcount + inc - own;
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                uint32_t j = tid * ITEMS + i;
+                if (j < k && sh.rl[j] == thr) A.run_scratch[at++] = sh.ent[j] - thr;
+            }
+            tcount += tot;
+            __syncthreads();
+        }
+        t_prev = thr;
+        first_epoch = false;
+    }
+    __syncthreads();
+    if (tid == c) sh.fill[c] = F + (uint32_t)O;
+    __syncthreads();
+    // ---- the terminals feed the other buckets through one ordinary small step
+    Seg ts;
+    ts.src = A.run_scratch; ts.pred = nullptr; ts.base = 0; ts.len = tcount; ts.rev = 0;
+    if (SPASS) { ts.lo = (c > 0) ? 0u : 1u; ts.hi = (c > 0) ? c - 1u : 0u; }
+    else       { ts.lo = c + 1u; ts.hi = 255u; }
+    sh.base[tid] = sh.fill[tid];
+    __syncthreads();
+    induce_tile<SPASS, MODE_SMALL, BITS>(A, sh, ts, 0);
+    sh.fill[tid] = sh.base[tid];
+    __syncthreads();
+}
+
 template <bool SPASS, int BITS>
 __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
     __shared__ IndShared sh;
@@ -183,7 +345,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
     if (BITS < 8 && tid < 16) sh.alpha[tid] = A.alpha[tid];
     uint32_t lastc = A.text[A.n - 1];
     sh.fill[tid] = (!SPASS && tid == lastc) ? 1u : 0u;
-    if (tid == 0) { sh.st_c = SPASS ? 255 : 0; sh.st_phase = 0; sh.st_begin = 0; }
+    if (tid == 0) { sh.st_c = SPASS ? 255 : 0; sh.st_phase = 0; sh.st_begin = 0; sh.streak = 0; sh.streak_c = -1; }
     __syncthreads();
     if (!SPASS && bid == 0 && tid == 0) A.sa[sh.bstart[lastc]] = A.n - 1u;
     uint32_t bigcount = 0;
@@ -197,6 +359,22 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
             if (bid == 0) {
                 while (sh.has && sh.seg.len <= (uint32_t)TILE) {
                     Seg g = sh.seg;
+                    const bool chain = sh.is_chain != 0;
+                    const int32_t cc = sh.ns_c;                 // a chain segment keeps ns_c == its bucket
+                    __syncthreads();
+                    if (tid == 0) {
+                        if (chain && sh.streak_c == cc) sh.streak++;
+                        else { sh.streak = chain ? 1u : 0u; sh.streak_c = chain ? cc : -1; }
+                    }
+                    __syncthreads();
+                    if (chain && sh.streak >= RUN_STREAK) {
+                        induce_run_skip<SPASS, BITS>(A, sh, g, (uint32_t)cc);
+                        if (tid == 0) { sh.st_c = cc; sh.st_phase = 0; sh.st_begin = sh.fill[cc]; sh.streak = 0; sh.streak_c = -1; }
+                        __syncthreads();
+                        if (tid == 0) induce_peek<SPASS>(A, sh);
+                        __syncthreads();
+                        continue;
+                    }
                     sh.base[tid] = sh.fill[tid];
                     __syncthreads();
                     induce_tile<SPASS, MODE_SMALL, BITS>(A, sh, g, 0);

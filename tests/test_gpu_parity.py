@@ -95,6 +95,35 @@ def test_medium_vs_oracle(ctx, maker, n):
         assert np.array_equal(lcp, oracle.lcp_kasai(t, want))
 
 
+def _long_run_cases():
+    rng = np.random.default_rng(99)
+    d = gen.dna(600_000)
+    out = [("a^2M", np.full(2_000_000, 97, dtype=np.uint8)),
+           ("zeros_ff", np.concatenate([np.zeros(1_500_000, dtype=np.uint8), np.full(1_500_000, 255, dtype=np.uint8)])),
+           ("ff_zeros", np.concatenate([np.full(1_500_000, 255, dtype=np.uint8), np.zeros(1_500_000, dtype=np.uint8)]))]
+    # poly-N genome shape: DNA with a few very long and many short N runs
+    parts = []
+    for k in range(40):
+        parts.append(d[k * 15000:(k + 1) * 15000])
+        parts.append(np.full(int(rng.choice([1, 3, 70, 500, 4097, 65, 300_000 if k % 13 == 0 else 9])), ord("N"), dtype=np.uint8))
+    out.append(("polyN", np.concatenate(parts)))
+    # runs of the SMALLEST and of a MIDDLE symbol, ending the text with a run
+    parts = []
+    for k in range(30):
+        parts.append(d[k * 7000:(k + 1) * 7000])
+        parts.append(np.full(int(rng.choice([2, 64, 65, 4096, 100_000])), ord("A") if k % 2 else ord("G"), dtype=np.uint8))
+    out.append(("polyA_G_tail", np.concatenate(parts)))
+    return out
+
+
+@pytest.mark.parametrize("name,t", _long_run_cases(), ids=lambda x: x if isinstance(x, str) else "")
+def test_long_runs(ctx, name, t):
+    """Run skipping in the induce: chains along runs of 10^5..10^6 equal bytes."""
+    t = np.ascontiguousarray(t)
+    sa = ctx.build(t)
+    assert np.array_equal(sa, oracle.sais(t)), name
+
+
 def _check_sa_properties(t, sa, samples=200000, seed=1):
     """Size-independent properties: permutation + sampled adjacent order."""
     n = len(t)
