@@ -68,7 +68,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._pump, daemon=True)
             self.thr.start()
         except Exception:
@@ -267,13 +267,22 @@ def run_gpu(args):
                 traffic = None
         phase_ms = {k: round(statistics.mean(v), 3) for k, v in phase_acc.items()}
         dom_share = (sum(ind.values()) / (ms_dev / steps)) if ind else None
+        # per-phase achieved GB/s against the same peak (SURVEY.md Appendix D bytes, level 0, w = 1)
+        appd = {"classify": 2 * n, "lms_group": 9 * m, "induce1_L": bytes_L, "induce1_S": bytes_S,
+                "induce2_L": bytes_L, "induce2_S": bytes_S, "compact_lms": 4 * n + n / 8 + 4 * m,
+                "name": 8 * n + 4 * m, "unrename": 16 * m, "lcp_phi": 8 * n, "lcp_plcp": 12 * n, "lcp_gather": 12 * n}
+        phases_roof = {}
+        for k, b in appd.items():
+            if k in phase_ms and phase_ms[k] > 0:
+                g = b / 1e9 / (phase_ms[k] / 1e3)
+                phases_roof[k] = {"GBps": round(g, 1), "frac": round(g / peak, 4)}
         roof = {"bound": "hbm", "kernel": "k_induce<L|S> (mean of the 4 persistent launches per build)",
                 "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg),
                 "kernel_ms_per_launch": round(ind_ms, 4) if ind_ms else None,
                 "share_of_step": round(dom_share, 3) if dom_share else None,
-                "pipeline_bytes_per_input_byte_compulsory": 14}
+                "pipeline_bytes_per_input_byte_compulsory": 14, "phases": phases_roof}
         # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
         cpu = None
         if world == 1 and not args.no_cpu:

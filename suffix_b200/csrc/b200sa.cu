@@ -585,6 +585,25 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
         TRY(read_words(c, sm + 3, 1));
         TRY(pack_text(c, text, n, c->h_pin[0]));
     }
+    // fast path: direct adjacent-pair compare when the text is L2-resident
+    // (packed, or small); falls through to the linear path if any pair hits the cap
+    if ((c->bits < 8 || n <= (32u << 20)) && !getenv("B200SA_LCP_LINEAR")) {
+        TRY(mark(c, "lcp_direct"));
+        uint32_t *sm = ptr<uint32_t>(c->small);
+        TRY(ensure(c, c->small, 4096));
+        sm = ptr<uint32_t>(c->small);
+        CU_TRY(c, cudaMemsetAsync(sm + 8, 0, 4, c->stream));
+        const uint32_t cap = 256;
+        if (c->bits == 2) LAUNCH(c, (k_lcp_direct<2>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
+        else if (c->bits == 4) LAUNCH(c, (k_lcp_direct<4>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
+        else LAUNCH(c, (k_lcp_direct<8>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
+        TRY(read_words(c, sm + 8, 1));
+        if (c->h_pin[0] == 0) {
+            TRY(mark(c, "end"));
+            CU_TRY(c, cudaGetLastError());
+            return B200SA_OK;
+        }
+    }
     TRY(mark(c, "lcp_phi"));
     if (n >= (1u << 22) && !getenv("B200SA_PHI_DIRECT")) {
         // partition (sa[r], sa[r-1]) by the top byte of sa[r], then scatter window by window

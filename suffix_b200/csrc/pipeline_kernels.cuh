@@ -224,6 +224,26 @@ __global__ void __launch_bounds__(BLK) k_pair_keys(const uint32_t *agrp, const u
 //   phi[sa[r]] = sa[r-1]            (one random write per suffix)
 //   plcp[i]    = lcp(i, phi[i])     (text order; plcp[i] >= plcp[i-1]-1)
 //   lcp[r]     = plcp[sa[r]]        (one random read per suffix)
+// Fast path: the reference's own definition, lcp_len(suffix sa[r-1], suffix sa[r])
+// (src/table.rs:356-365), evaluated directly per adjacent pair with word-wide
+// compares on the (L2-resident) packed text, capped at `cap` chars.  Pairs that
+// reach the cap are counted; if any exist the caller recomputes everything with
+// the linear Phi/PLCP path below (the direct form is quadratic on repetitive text).
+template <int BITS>
+__global__ void __launch_bounds__(BLK) k_lcp_direct(const void *__restrict__ ptext, uint32_t n,
+                                                    const uint32_t *__restrict__ sa, uint32_t *lcp, uint32_t cap,
+                                                    uint32_t *capped) {
+    uint32_t r = blockIdx.x * BLK + threadIdx.x;
+    if (r >= n) return;
+    if (r == 0) { lcp[0] = 0; return; }
+    uint32_t a = sa[r - 1], b = sa[r];
+    uint32_t room = n - (a > b ? a : b);
+    uint32_t limit = room < cap ? room : cap;
+    uint32_t h = text_match<BITS>(ptext, a, b, limit);
+    lcp[r] = h;
+    if (h == cap && room > cap) atomicAdd(capped, 1u);
+}
+
 constexpr uint32_t PHI_NONE = 0xffffffffu;
 __global__ void __launch_bounds__(BLK) k_phi(const uint32_t *__restrict__ sa, uint32_t n, uint32_t *phi) {
     uint32_t r = blockIdx.x * BLK + threadIdx.x;

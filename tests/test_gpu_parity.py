@@ -95,6 +95,21 @@ def test_medium_vs_oracle(ctx, maker, n):
         assert np.array_equal(lcp, oracle.lcp_kasai(t, want))
 
 
+@pytest.mark.parametrize("maker", ["dna", "bytes", "fixture"])
+def test_lcp_both_paths(ctx, maker, monkeypatch):
+    """lcp_lens has a direct fast path (the reference's per-pair lcp_len, capped)
+    and the linear Phi/PLCP path; both must give the reference's array."""
+    t = {"dna": lambda: gen.dna(2_000_000), "bytes": lambda: gen.rand_bytes(2_000_000),
+         "fixture": lambda: gen.fixture("AP009048_100000.fasta")}[maker]()
+    want_sa = oracle.sais(t)
+    want = oracle.lcp_kasai(t, want_sa)
+    assert np.array_equal(ctx.lcp(t, want_sa), want)
+    monkeypatch.setenv("B200SA_LCP_LINEAR", "1")
+    assert np.array_equal(ctx.lcp(t, want_sa), want)
+    monkeypatch.setenv("B200SA_PHI_DIRECT", "1")
+    assert np.array_equal(ctx.lcp(t, want_sa), want)
+
+
 def _long_run_cases():
     rng = np.random.default_rng(99)
     d = gen.dna(600_000)
