@@ -513,8 +513,14 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
         TRY(ensure(c, c->sa_r, (size_t)m * 4));
         TRY(ensure(c, c->rank, (size_t)m * 4));
         TRY(ensure(c, c->g1, (size_t)m * 4));
+        // first refinement: k-gram of dense names (reduced string), k = as many as fit 64 bits
+        uint32_t bw = (uint32_t)bit_length(names);
+        uint32_t kgram = bw ? 64u / bw : 0u;
+        if (kgram > 8) kgram = 8;
+        if (const char *e = getenv("B200SA_KGRAM")) { int v = atoi(e); if (v >= 0 && (uint32_t)v * bw <= 64) kgram = (uint32_t)v; }
         TRY((dev_scan<OpMax>(c, InFlagPos{ptr<uint8_t>(c->flag)},
                              OutInitFromSorted{ptr<uint32_t>(c->sorted), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank),
+                                               ptr<uint8_t>(c->flag), m, kgram >= 2 ? 0 : 1,
                                                ptr<uint32_t>(c->sa_r), ptr<uint32_t>(c->g1), ptr<uint32_t>(c->rank)},
                              m, nullptr)));
         if (names < m) {
@@ -529,11 +535,6 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
                                  m, sm)));
             TRY(read_words(c, sm, 1));
             uint32_t na = c->h_pin[0], rounds = 0;
-            // first refinement: k-gram of dense names (reduced string), k = as many as fit 64 bits
-            uint32_t bw = (uint32_t)bit_length(names);
-            uint32_t kgram = bw ? 64u / bw : 0u;
-            if (kgram > 8) kgram = 8;
-            if (const char *e = getenv("B200SA_KGRAM")) { int v = atoi(e); if (v >= 0 && (uint32_t)v * bw <= 64) kgram = (uint32_t)v; }
             TRY(doubling_rounds(c, m, na, ptr<uint32_t>(c->v0), ptr<uint32_t>(c->v1), 1, &rounds,
                                 ptr<uint32_t>(c->reduced), kgram, bw));
             c->stats.doubling_rounds = rounds;

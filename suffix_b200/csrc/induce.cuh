@@ -84,39 +84,71 @@ struct IndShared {
 
 enum { MODE_COUNT = 0, MODE_SCATTER = 1, MODE_SMALL = 2 };
 
-// Processes logical items [t0, t0+TILE) ∩ [0, g.len) of segment g.
-template <bool SPASS, int MODE, int BITS>
-__device__ __forceinline__ void induce_tile(const InduceArgs &A, IndShared &sh, const Seg &g, uint32_t t0) {
+// ---- tile pieces.  A tile is the logical items [t0, t0+TILE) ∩ [0, g.len) of
+// segment g in the warp-blocked layout of tile_rank.  The big-step loops below
+// prefetch the next tile's loads before working on the current one.
+__device__ __forceinline__ void tile_load_s(const Seg &g, uint32_t t0, uint32_t (&s)[ITEMS]) {
     const uint32_t w = warp_id(), l = lane_id();
-    uint32_t s[ITEMS], d[ITEMS], rank[ITEMS], vm = 0;
-    if (MODE != MODE_COUNT) {
-#pragma unroll
-        for (int ww = 0; ww < NWARP; ww++) sh.wcnt[ww][threadIdx.x] = 0;
-        __syncthreads();
-    }
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         uint32_t k = t0 + w * (ITEMS * 32) + r * 32 + l;
-        bool in = k < g.len;
         uint32_t p = g.rev ? g.base - k : g.base + k;
-        s[r] = in ? __ldcg(g.src + p) : 0u;
+        s[r] = (k < g.len) ? __ldcg(g.src + p) : 0u;
     }
+}
+__device__ __forceinline__ void tile_load_pred(const Seg &g, uint32_t t0, uint32_t (&d)[ITEMS]) {
+    const uint32_t w = warp_id(), l = lane_id();
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         uint32_t k = t0 + w * (ITEMS * 32) + r * 32 + l;
-        bool in = k < g.len;
         uint32_t p = g.rev ? g.base - k : g.base + k;
-        if (MODE == MODE_SCATTER) d[r] = in ? (uint32_t)__ldcg(g.pred + p) : 0u;
-        else if (BITS == 8) d[r] = (s[r] > 0) ? text_get<8>(A.ptext, s[r] - 1) : 0u;
+        d[r] = (k < g.len) ? (uint32_t)__ldcg(g.pred + p) : 0u;
+    }
+}
+template <int BITS>
+__device__ __forceinline__ void tile_gather(const InduceArgs &A, const IndShared &sh, const uint32_t (&s)[ITEMS],
+                                            uint32_t (&d)[ITEMS]) {
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        if (BITS == 8) d[r] = (s[r] > 0) ? text_get<8>(A.ptext, s[r] - 1) : 0u;
         else d[r] = (s[r] > 0) ? sh.alpha[text_get<BITS>(A.ptext, s[r] - 1)] : 0u;
-        bool valid = in && s[r] > 0 && d[r] >= g.lo && d[r] <= g.hi;
-        vm |= (valid ? 1u : 0u) << r;
-        if (MODE == MODE_COUNT) {
-            if (in) g.pred[p] = (uint8_t)d[r];
-            hist_add(sh.hist, d[r], valid);
-        }
     }
-    if (MODE == MODE_COUNT) return;
+}
+__device__ __forceinline__ uint32_t tile_valid(const Seg &g, uint32_t t0, const uint32_t (&s)[ITEMS],
+                                               const uint32_t (&d)[ITEMS]) {
+    const uint32_t w = warp_id(), l = lane_id();
+    uint32_t vm = 0;
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        uint32_t k = t0 + w * (ITEMS * 32) + r * 32 + l;
+        bool valid = k < g.len && s[r] > 0 && d[r] >= g.lo && d[r] <= g.hi;
+        vm |= (valid ? 1u : 0u) << r;
+    }
+    return vm;
+}
+// count phase of a big step: remember T[s-1] per slot, histogram the valid ones
+__device__ __forceinline__ void tile_count(IndShared &sh, const Seg &g, uint32_t t0, const uint32_t (&s)[ITEMS],
+                                           const uint32_t (&d)[ITEMS]) {
+    const uint32_t w = warp_id(), l = lane_id();
+    uint32_t vm = tile_valid(g, t0, s, d);
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        uint32_t k = t0 + w * (ITEMS * 32) + r * 32 + l;
+        uint32_t p = g.rev ? g.base - k : g.base + k;
+        if (k < g.len) g.pred[p] = (uint8_t)d[r];
+        hist_add(sh.hist, d[r], (vm >> r) & 1u);
+    }
+}
+// stable scatter of one tile (s, d given); advances sh.base by the tile's counts
+template <bool SPASS>
+__device__ __forceinline__ void tile_scatter(const InduceArgs &A, IndShared &sh, const Seg &g, uint32_t t0,
+                                             const uint32_t (&s)[ITEMS], const uint32_t (&d)[ITEMS]) {
+    const uint32_t w = warp_id();
+    uint32_t rank[ITEMS];
+#pragma unroll
+    for (int ww = 0; ww < NWARP; ww++) sh.wcnt[ww][threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t vm = tile_valid(g, t0, s, d);
     tile_rank(d, vm, rank, sh.wcnt, sh.tcnt);
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
@@ -129,6 +161,14 @@ __device__ __forceinline__ void induce_tile(const InduceArgs &A, IndShared &sh, 
     __syncthreads();
     sh.base[threadIdx.x] += sh.tcnt[threadIdx.x];
     __syncthreads();
+}
+// one whole tile in a small step (block 0): load, gather, scatter
+template <bool SPASS, int MODE, int BITS>
+__device__ __forceinline__ void induce_tile(const InduceArgs &A, IndShared &sh, const Seg &g, uint32_t t0) {
+    uint32_t s[ITEMS], d[ITEMS];
+    tile_load_s(g, t0, s);
+    tile_gather<BITS>(A, sh, s, d);
+    tile_scatter<SPASS>(A, sh, g, t0, s, d);
 }
 
 // Thread 0: derive the next non-empty segment from (state, fill) without
@@ -410,7 +450,17 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
         // phase A: count + remember predecessors
         sh.hist[tid] = 0;
         __syncthreads();
-        for (uint32_t t = tb0; t < tb1; t++) induce_tile<SPASS, MODE_COUNT, BITS>(A, sh, g, t * TILE);
+        if (tb0 < tb1) {
+            uint32_t s_cur[ITEMS], s_nxt[ITEMS], d_cur[ITEMS];
+            tile_load_s(g, tb0 * TILE, s_cur);
+            for (uint32_t t = tb0; t < tb1; t++) {
+                if (t + 1 < tb1) tile_load_s(g, (t + 1) * TILE, s_nxt);      // prefetch under the gather
+                tile_gather<BITS>(A, sh, s_cur, d_cur);
+                tile_count(sh, g, t * TILE, s_cur, d_cur);
+#pragma unroll
+                for (int r = 0; r < ITEMS; r++) s_cur[r] = s_nxt[r];
+            }
+        }
         __syncthreads();
         if (bid < nact) cntbuf[(size_t)bid * 256u + tid] = sh.hist[tid];
         grid.sync();
@@ -424,7 +474,20 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
             }
             sh.base[tid] = base;
             __syncthreads();
-            for (uint32_t t = tb0; t < tb1; t++) induce_tile<SPASS, MODE_SCATTER, BITS>(A, sh, g, t * TILE);
+            if (tb0 < tb1) {
+                uint32_t s_cur[ITEMS], d_cur[ITEMS], s_nxt[ITEMS], d_nxt[ITEMS];
+                tile_load_s(g, tb0 * TILE, s_cur);
+                tile_load_pred(g, tb0 * TILE, d_cur);
+                for (uint32_t t = tb0; t < tb1; t++) {
+                    if (t + 1 < tb1) {                                        // prefetch under the ranking
+                        tile_load_s(g, (t + 1) * TILE, s_nxt);
+                        tile_load_pred(g, (t + 1) * TILE, d_nxt);
+                    }
+                    tile_scatter<SPASS>(A, sh, g, t * TILE, s_cur, d_cur);
+#pragma unroll
+                    for (int r = 0; r < ITEMS; r++) { s_cur[r] = s_nxt[r]; d_cur[r] = d_nxt[r]; }
+                }
+            }
             __syncthreads();
             sh.fill[tid] += tot;
         }

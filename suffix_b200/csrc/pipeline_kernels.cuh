@@ -98,14 +98,18 @@ struct InFlagPos {
     __device__ uint32_t operator()(uint64_t i) const { return f[i] ? (uint32_t)i : 0u; }
 };
 struct OutInitFromSorted {
-    const uint32_t *sorted; const uint32_t *lmsb; const uint32_t *lmsrank;
+    const uint32_t *sorted; const uint32_t *lmsb; const uint32_t *lmsrank; const uint8_t *flag; uint32_t m; int write_all;
     uint32_t *sa_r; uint32_t *grp; uint32_t *rank;
     __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const {
         uint32_t g = exc > v ? exc : v;
         uint32_t tr = lms_text_rank(lmsb, lmsrank, sorted[i]);
         sa_r[i] = tr;
         grp[i] = g;
-        rank[tr] = g + 1u;
+        // members of larger groups get their rank from the first refinement round,
+        // which sorts all of them; only name-singletons need it now (saves the
+        // random scatter for ~98 % of a DNA-like reduced string)
+        bool single = flag[i] && (i + 1 == m || flag[i + 1]);
+        if (single || write_all) rank[tr] = g + 1u;
     }
 };
 // K9: all names unique -> SA of the reduced string is the inverse permutation
