@@ -54,54 +54,70 @@ def _peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks/throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons of one GPU through NVML every few
+    milliseconds on a thread; only samples taken inside a marked window count."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.lines = []
-        self.proc = None
+        self.samples = []          # (t, sm_mhz, reasons_bitmask)
+        self.windows = []
+        self.stop_flag = False
+        self.ok = False
+        self.thr = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical order; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.thr = threading.Thread(target=self._loop, daemon=True)
             self.thr.start()
         except Exception:
-            self.proc = None
+            self.ok = False
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self.stop_flag = True
+        self.thr.join(timeout=2)
+        inside = [(m, r) for (t, m, r) in self.samples if any(a <= t <= b for a, b in self.windows)]
+        reasons = set()
+        for _, r in inside:
+            for nm, bit in self.REASONS.items():
+                if r & bit:
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median([m for m, _ in inside]) if inside else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(inside), "reasons": sorted(reasons),
+                "how": "NVML polled every ~4 ms during the timed regions (device-resident and e2e loops)"}
 
 
 def _dist_env():
@@ -199,6 +215,7 @@ def run_gpu(args):
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase_acc, launches = {}, 0
+    tw0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(steps):
         ph, ph2, l = step_dev()
@@ -207,8 +224,8 @@ def run_gpu(args):
             phase_acc.setdefault(k, []).append(v)
     ev1.record(stream)
     barrier()
+    sampler.window(tw0, time.perf_counter())
     ms_dev = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     stats = ctx.stats()
     # SA-only share from the library's own phase events (same timed region)
     sa_ms = sum(sum(v) for k, v in phase_acc.items() if not k.startswith("lcp")) / steps
@@ -232,6 +249,8 @@ def run_gpu(args):
         step_host()                       # synchronous: returns with SA/LCP in host memory
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
+    sampler.window(t0, time.perf_counter())
+    clocks = sampler.stop() if rank == 0 else None
     e2e_result_check = int(h_lcp[0].item()) + int(h_sa[0].item() >= 0)   # touch the result
 
     # ---------------- max over ranks
