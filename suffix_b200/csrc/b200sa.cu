@@ -154,14 +154,15 @@ static int read_words(b200sa_ctx *c, const uint32_t *dsrc, int count) {
 
 // ------------------------------------------------------- generic primitives
 template <class Op, class InF, class OutF>
-static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, uint32_t *d_total) {
+static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, typename Op::T *d_total) {
+    typedef typename Op::T T;
     if (n == 0) {
-        if (d_total) CU_TRY(c, cudaMemsetAsync(d_total, 0, 4, c->stream));
+        if (d_total) CU_TRY(c, cudaMemsetAsync(d_total, 0, sizeof(T), c->stream));
         return B200SA_OK;
     }
     uint32_t nb = cdiv(n, SCAN_CHUNK);
-    TRY(ensure(c, c->scan_partial, (size_t)nb * 4));
-    uint32_t *part = ptr<uint32_t>(c->scan_partial);
+    TRY(ensure(c, c->scan_partial, (size_t)nb * sizeof(T)));
+    T *part = ptr<T>(c->scan_partial);
     LAUNCH(c, (k_scan_reduce<Op, InF>), nb, in, n, part);
     LAUNCH(c, (k_scan_partials<Op>), 1, part, nb, d_total);
     LAUNCH(c, (k_scan_apply<Op, InF, OutF>), nb, in, out, n, part);
@@ -217,7 +218,13 @@ static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, u
     uint32_t *ticket = ghist + OS_MAX_PASSES * 256;
     CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
     uint32_t hb = tiles < 1184u ? tiles : 1184u;
-    LAUNCH(c, (k_os_hist<K, LoadArr<K>>), hb, LoadArr<K>{ka}, n, npass, 0u, ghist);
+    {
+        size_t shm = (size_t)NWARP * npass * 256 * 4;
+        auto kfn = k_os_hist<K, LoadArr<K>>;
+        CU_TRY(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NWARP * OS_MAX_PASSES * 256 * 4)));
+        kfn<<<hb, BLK, shm, c->stream>>>(LoadArr<K>{ka}, n, npass, 0u, ghist);
+        c->launches++;
+    }
     LAUNCH(c, k_os_scan, (uint32_t)npass, ghist);
     for (int p = 0; p < npass; p++) {
         CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
@@ -277,9 +284,10 @@ static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asu
         TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, bits, &K2, &Vsorted));
         uint32_t *Vother = (Vsorted == asuf) ? ascratch : asuf;
         { uint32_t ri = rounds - *rounds_io; TRY(mark(c, kScanNames[ri <= 5 ? ri - 1 : 5])); }
-        TRY((dev_scan<OpMax>(c, InGroupStart<uint64_t>{K2, apos}, OutGroupRank{Vsorted, apos, G1, rank, sa_r}, na, nullptr)));
-        TRY((dev_scan<OpSum>(c, InActive<uint64_t>{K2, na}, OutCompactActive{apos, Vsorted, G1, apos_next, Vother, G0}, na, d_na)));
-        TRY(read_words(c, d_na, 1));
+        TRY((dev_scan<OpMaxSum>(c, InGroupActive<uint64_t>{K2, apos, na},
+                                OutGroupRankCompact{Vsorted, apos, rank, sa_r, apos_next, Vother, G0}, na,
+                                reinterpret_cast<unsigned long long *>(d_na + 16))));
+        TRY(read_words(c, d_na + 16, 1));          // low word of the pair total = number of ambiguous suffixes
         na = c->h_pin[0];
         if (getenv("B200SA_TRACE")) fprintf(stderr, "[b200sa] doubling round %u: h=%llu -> active %u of %u\n", rounds, (unsigned long long)h, na, m);
         asuf = Vother; ascratch = Vsorted;

@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(BLK) k_cls_types(const uint8_t *__restrict__ t
                                                    uint32_t *hist768, ShardEdge edge) {
     __shared__ uint32_t s_warp[NWARP];
     __shared__ uint32_t s_sw[BLK];
-    __shared__ uint32_t s_hist[768];
-    for (int k = threadIdx.x; k < 768; k += BLK) s_hist[k] = 0;
+    __shared__ uint32_t s_hist[NWARP][768];        // per-warp private: plain RMW instead of ATOMS
+    for (int k = threadIdx.x; k < NWARP * 768; k += BLK) (&s_hist[0][0])[k] = 0;
     uint64_t w = (uint64_t)blockIdx.x * CLS_WORDS + threadIdx.x;
     uint64_t nw = (n + 31) / 32;
     uint32_t c[8], nextc, lt, gt;
@@ -185,11 +185,13 @@ __global__ void __launch_bounds__(BLK) k_cls_types(const uint8_t *__restrict__ t
     for (int j = 0; j < 32; j++) {
         bool valid = (uint32_t)j < cnt;
         uint32_t cls = ((sw >> j) & 1u) + ((lw >> j) & 1u);
-        hist_add(s_hist, byte_of(c, j) + 256u * cls, valid);
+        hist_add_private<10>(s_hist[warp_id()], byte_of(c, j) + 256u * cls, valid);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < 768; k += BLK) {
-        uint32_t v = s_hist[k];
+        uint32_t v = 0;
+#pragma unroll
+        for (int ww = 0; ww < NWARP; ww++) v += s_hist[ww][k];
         if (v) atomicAdd(&hist768[k], v);
     }
 }

@@ -20,21 +20,57 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+// Lanes of the warp that hold the same NBITS-bit key (and are valid), built from
+// NBITS+1 ballots.  MATCH.ANY iterates over the distinct values of a warp (up to
+// 32 for random digits); the ballot form is a fixed, short sequence.  Measured
+// (profiles/README.md, exp3): ballots win ~25 % on random bytes, lose ~35 % on
+// 4-symbol DNA and cost registers in k_induce, so MATCH stays the default.
+#ifndef PEERS_MATCH
+#define PEERS_MATCH 1
+#endif
+template <int NBITS>
+__device__ __forceinline__ uint32_t peer_mask(uint32_t key, bool valid) {
+#if PEERS_MATCH
+    return __match_any_sync(FULL, valid ? key : 0xffffffffu) & __ballot_sync(FULL, valid);
+#else
+    uint32_t peers = __ballot_sync(FULL, valid);
+#pragma unroll
+    for (int b = 0; b < NBITS; b++) {
+        bool bit = (key >> b) & 1u;
+        uint32_t bal = __ballot_sync(FULL, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+#endif
+}
+
 // ---------------------------------------------------------------- scan ops
 struct OpSum {
+    using T = uint32_t;
     __device__ __forceinline__ static uint32_t id() { return 0u; }
     __device__ __forceinline__ static uint32_t op(uint32_t a, uint32_t b) { return a + b; }
 };
 struct OpMax {
+    using T = uint32_t;
     __device__ __forceinline__ static uint32_t id() { return 0u; }
     __device__ __forceinline__ static uint32_t op(uint32_t a, uint32_t b) { return a > b ? a : b; }
 };
 
+// pair scan: max over the high word, sum over the low word (group start + active count in one pass)
+struct OpMaxSum {
+    using T = unsigned long long;
+    __device__ __forceinline__ static T id() { return 0ull; }
+    __device__ __forceinline__ static T op(T a, T b) {
+        uint32_t ah = (uint32_t)(a >> 32), bh = (uint32_t)(b >> 32);
+        return ((T)(ah > bh ? ah : bh) << 32) | (uint32_t)((uint32_t)a + (uint32_t)b);
+    }
+};
+
 template <class Op>
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+__device__ __forceinline__ typename Op::T warp_incl_scan(typename Op::T v) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(FULL, v, o);
+        typename Op::T t = __shfl_up_sync(FULL, v, o);
         if ((int)lane_id() >= o) v = Op::op(v, t);
     }
     return v;
@@ -43,15 +79,16 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 // Block-wide inclusive scan of one value per thread.  s_w: NWARP+1 words of
 // shared memory.  Returns the inclusive result; *total gets the block total.
 template <class Op>
-__device__ __forceinline__ uint32_t block_incl_scan(uint32_t v, uint32_t *s_w, uint32_t *total) {
-    uint32_t inc = warp_incl_scan<Op>(v);
+__device__ __forceinline__ typename Op::T block_incl_scan(typename Op::T v, typename Op::T *s_w, typename Op::T *total) {
+    typedef typename Op::T T;
+    T inc = warp_incl_scan<Op>(v);
     __syncthreads();                       // protect s_w from a previous use
     if (lane_id() == 31) s_w[warp_id()] = inc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t run = Op::id();
+        T run = Op::id();
         for (int w = 0; w < NWARP; w++) {
-            uint32_t t = s_w[w];
+            T t = s_w[w];
             s_w[w] = run;                  // exclusive prefix of warp w
             run = Op::op(run, t);
         }
@@ -70,35 +107,34 @@ constexpr int SCAN_IPT = 16;
 constexpr int SCAN_CHUNK = BLK * SCAN_IPT;   // 4096
 
 template <class Op, class InF>
-__global__ void __launch_bounds__(BLK) k_scan_reduce(InF in, uint64_t n, uint32_t *partial) {
-    __shared__ uint32_t s_w[NWARP + 1];
+__global__ void __launch_bounds__(BLK) k_scan_reduce(InF in, uint64_t n, typename Op::T *partial) {
+    typedef typename Op::T T;
+    __shared__ T s_w[NWARP + 1];
     uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK;
-    uint32_t acc = Op::id();
+    T acc = Op::id();
 #pragma unroll 4
     for (int k = 0; k < SCAN_IPT; k++) {
         uint64_t i = base + (uint64_t)k * BLK + threadIdx.x;
         if (i < n) acc = Op::op(acc, in(i));
     }
-    uint32_t total;
+    T total;
     block_incl_scan<Op>(acc, s_w, &total);
     if (threadIdx.x == 0) partial[blockIdx.x] = total;
 }
 
 // Single block: in-place exclusive scan of partial[0..nb); total -> *out_total.
 template <class Op>
-__global__ void __launch_bounds__(BLK) k_scan_partials(uint32_t *partial, uint32_t nb, uint32_t *out_total) {
-    __shared__ uint32_t s_w[NWARP + 1];
-    uint32_t carry = Op::id();
+__global__ void __launch_bounds__(BLK) k_scan_partials(typename Op::T *partial, uint32_t nb, typename Op::T *out_total) {
+    typedef typename Op::T T;
+    __shared__ T s_w[NWARP + 1];
+    T carry = Op::id();
     for (uint32_t b0 = 0; b0 < nb; b0 += BLK) {
         uint32_t i = b0 + threadIdx.x;
-        uint32_t v = i < nb ? partial[i] : Op::id();
-        uint32_t total;
-        uint32_t inc = block_incl_scan<Op>(v, s_w, &total);
-        // exclusive = carry op (inclusive without own value); recompute via shuffle-free trick
-        uint32_t prev = __shfl_up_sync(FULL, inc, 1);
-        uint32_t exc;
-        if (lane_id() == 0) exc = s_w[warp_id()];          // exclusive prefix of this warp
-        else exc = prev;
+        T v = i < nb ? partial[i] : Op::id();
+        T total;
+        T inc = block_incl_scan<Op>(v, s_w, &total);
+        T prev = __shfl_up_sync(FULL, inc, 1);
+        T exc = (lane_id() == 0) ? s_w[warp_id()] : prev;       // exclusive prefix inside the chunk
         if (i < nb) partial[i] = Op::op(carry, exc);
         carry = Op::op(carry, total);
         __syncthreads();
@@ -110,33 +146,34 @@ __global__ void __launch_bounds__(BLK) k_scan_partials(uint32_t *partial, uint32
 // chunk, read in SCAN_IPT coalesced rounds of 32; each round is one warp scan
 // with a running carry, then one cross-warp fix-up.
 template <class Op, class InF, class OutF>
-__global__ void __launch_bounds__(BLK) k_scan_apply(InF in, OutF out, uint64_t n, const uint32_t *partial_excl) {
-    __shared__ uint32_t s_w[NWARP + 1];
+__global__ void __launch_bounds__(BLK) k_scan_apply(InF in, OutF out, uint64_t n, const typename Op::T *partial_excl) {
+    typedef typename Op::T T;
+    __shared__ T s_w[NWARP + 1];
     const uint32_t w = warp_id(), l = lane_id();
     uint64_t base = (uint64_t)blockIdx.x * SCAN_CHUNK + (uint64_t)w * (SCAN_IPT * 32) + l;
-    uint32_t v[SCAN_IPT], exc[SCAN_IPT];
-    uint32_t carry = Op::id();
+    T v[SCAN_IPT], exc[SCAN_IPT];
+    T carry = Op::id();
 #pragma unroll
     for (int k = 0; k < SCAN_IPT; k++) {
         uint64_t i = base + (uint64_t)k * 32;
-        v[k] = (i < n) ? in(i) : Op::id();
-        uint32_t inc = warp_incl_scan<Op>(v[k]);
-        uint32_t prev = __shfl_up_sync(FULL, inc, 1);
+        v[k] = (i < n) ? (T)in(i) : Op::id();
+        T inc = warp_incl_scan<Op>(v[k]);
+        T prev = __shfl_up_sync(FULL, inc, 1);
         exc[k] = Op::op(carry, l == 0 ? Op::id() : prev);
         carry = Op::op(carry, __shfl_sync(FULL, inc, 31));
     }
     if (l == 0) s_w[w] = carry;           // warp total
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t run = partial_excl[blockIdx.x];
+        T run = partial_excl[blockIdx.x];
         for (int ww = 0; ww < NWARP; ww++) {
-            uint32_t t = s_w[ww];
+            T t = s_w[ww];
             s_w[ww] = run;
             run = Op::op(run, t);
         }
     }
     __syncthreads();
-    uint32_t wbase = s_w[w];
+    T wbase = s_w[w];
 #pragma unroll
     for (int k = 0; k < SCAN_IPT; k++) {
         uint64_t i = base + (uint64_t)k * 32;
@@ -159,8 +196,7 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&dig)[ITEMS], uint32_t
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         bool valid = (validmask >> r) & 1u;
-        uint32_t key = valid ? dig[r] : 0x100u;
-        uint32_t peers = __match_any_sync(FULL, key);
+        uint32_t peers = peer_mask<8>(dig[r], valid);
         uint32_t below = __popc(peers & lt);
         uint32_t base = valid ? s_wcnt[w][dig[r]] : 0u;
         __syncwarp();
@@ -184,10 +220,20 @@ __device__ __forceinline__ void tile_rank(const uint32_t (&dig)[ITEMS], uint32_t
 }
 
 // Warp-aggregated shared-memory histogram increment (all 32 lanes must call).
+template <int NBITS = 8>
 __device__ __forceinline__ void hist_add(uint32_t *s_hist, uint32_t key, bool valid) {
-    uint32_t k = valid ? key : 0xffffffffu;
-    uint32_t peers = __match_any_sync(FULL, k);
+    uint32_t peers = peer_mask<NBITS>(key, valid);
     if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&s_hist[key], (uint32_t)__popc(peers));
+}
+
+// Same aggregation into a histogram that is PRIVATE to the calling warp: the
+// leader lanes hold distinct keys, so a plain read-modify-write replaces the
+// shared-memory atomic (ATOMS costs ~2 cycles per lane on this part).
+template <int NBITS = 8>
+__device__ __forceinline__ void hist_add_private(uint32_t *s_warp_hist, uint32_t key, bool valid) {
+    uint32_t peers = peer_mask<NBITS>(key, valid);
+    if (valid && (peers & lanemask_lt()) == 0) s_warp_hist[key] += (uint32_t)__popc(peers);
+    __syncwarp();
 }
 
 // ------------------------------------------------------------ radix passes
@@ -276,20 +322,26 @@ __device__ __forceinline__ void os_store(unsigned long long *p, unsigned long lo
 }
 constexpr int OS_MAX_PASSES = 8;
 
+// dynamic shared memory: [NWARP][npass][256] u32 (64 KB for 8 passes)
 template <class K, class KeyF>
 __global__ void __launch_bounds__(BLK) k_os_hist(KeyF keyf, uint64_t n, int npass, uint32_t shift0, uint32_t *ghist) {
-    __shared__ uint32_t s_h[OS_MAX_PASSES][256];
-    for (int p = 0; p < npass; p++) s_h[p][threadIdx.x] = 0;
+    extern __shared__ uint32_t s_dyn[];
+    const uint32_t w = warp_id();
+    for (int i = threadIdx.x; i < NWARP * npass * 256; i += BLK) s_dyn[i] = 0;
     __syncthreads();
+    uint32_t *mine = s_dyn + (size_t)w * npass * 256;
     for (uint64_t i0 = (uint64_t)blockIdx.x * BLK; i0 < n; i0 += (uint64_t)gridDim.x * BLK) {
         uint64_t i = i0 + threadIdx.x;
         bool valid = i < n;
         K key = valid ? keyf(i) : (K)0;
-        for (int p = 0; p < npass; p++) hist_add(s_h[p], (uint32_t)(key >> (shift0 + 8 * p)) & 0xffu, valid);
+        for (int p = 0; p < npass; p++)
+            hist_add_private(mine + p * 256, (uint32_t)(key >> (shift0 + 8 * p)) & 0xffu, valid);
     }
     __syncthreads();
     for (int p = 0; p < npass; p++) {
-        uint32_t v = s_h[p][threadIdx.x];
+        uint32_t v = 0;
+#pragma unroll
+        for (int ww = 0; ww < NWARP; ww++) v += s_dyn[((size_t)ww * npass + p) * 256 + threadIdx.x];
         if (v) atomicAdd(&ghist[p * 256 + threadIdx.x], v);
     }
 }

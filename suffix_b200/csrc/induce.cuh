@@ -136,7 +136,7 @@ __device__ __forceinline__ void tile_count(IndShared &sh, const Seg &g, uint32_t
         uint32_t k = t0 + w * (ITEMS * 32) + r * 32 + l;
         uint32_t p = g.rev ? g.base - k : g.base + k;
         if (k < g.len) g.pred[p] = (uint8_t)d[r];
-        hist_add(sh.hist, d[r], (vm >> r) & 1u);
+        hist_add_private(sh.wcnt[w], d[r], (vm >> r) & 1u);     // per-warp private counters
     }
 }
 // stable scatter of one tile (s, d given); advances sh.base by the tile's counts
@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
         uint32_t tb0 = bid * tpb, tb1 = tb0 + tpb;
         if (tb1 > tiles) tb1 = tiles;
         // phase A: count + remember predecessors
-        sh.hist[tid] = 0;
+#pragma unroll
+        for (int ww = 0; ww < NWARP; ww++) sh.wcnt[ww][tid] = 0;
         __syncthreads();
         if (tb0 < tb1) {
             uint32_t s_cur[ITEMS], s_nxt[ITEMS], d_cur[ITEMS];
@@ -462,7 +463,13 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
             }
         }
         __syncthreads();
-        if (bid < nact) cntbuf[(size_t)bid * 256u + tid] = sh.hist[tid];
+        if (bid < nact) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int ww = 0; ww < NWARP; ww++) v += sh.wcnt[ww][tid];
+            cntbuf[(size_t)bid * 256u + tid] = v;
+        }
+        __syncthreads();      // wcnt is reused by the scatter phase
         grid.sync();
         // phase B: offsets, scatter
         {

@@ -203,6 +203,36 @@ struct InActive {
         return (head && tail) ? 0u : 1u;
     }
 };
+// Fused per-round pass: one (max, sum) pair scan derives the group start of every
+// sorted element AND compacts the still-ambiguous ones (the two used to be separate
+// scans, each reading the keys twice).
+template <class K>
+struct InGroupActive {
+    const K *keys; const uint32_t *pos; uint64_t cnt;
+    __device__ unsigned long long operator()(uint64_t i) const {
+        bool head = (i == 0) || (keys[i] != keys[i - 1]);
+        bool tail = (i + 1 == cnt) || (keys[i + 1] != keys[i]);
+        uint32_t hi = head ? (pos ? pos[i] : (uint32_t)i) : 0u;
+        uint32_t lo = (head && tail) ? 0u : 1u;
+        return ((unsigned long long)hi << 32) | lo;
+    }
+};
+struct OutGroupRankCompact {
+    const uint32_t *suf; const uint32_t *pos; uint32_t *rank; uint32_t *sa_r;
+    uint32_t *opos; uint32_t *osuf; uint32_t *ogrp;
+    __device__ void operator()(uint64_t i, unsigned long long exc, unsigned long long v) const {
+        uint32_t eh = (uint32_t)(exc >> 32), vh = (uint32_t)(v >> 32);
+        uint32_t g = eh > vh ? eh : vh;
+        uint32_t s = suf[i];
+        uint32_t p = pos ? pos[i] : (uint32_t)i;
+        rank[s] = g + 1u;
+        if (sa_r) sa_r[p] = s;
+        if ((uint32_t)v) {                      // member of a group that is still ambiguous
+            uint32_t k = (uint32_t)exc;
+            opos[k] = p; osuf[k] = s; ogrp[k] = g;
+        }
+    }
+};
 struct OutCompactActive {
     const uint32_t *pos; const uint32_t *suf; const uint32_t *grp;   // pos==nullptr -> index
     uint32_t *opos; uint32_t *osuf; uint32_t *ogrp;
