@@ -15,8 +15,11 @@
  * There is NO CPU fallback: without a usable CUDA device every call returns
  * B200SA_ERR_NO_DEVICE / B200SA_ERR_CUDA.
  *
- * Suffix indices are byte offsets stored as u32 (reference: src/table.rs:64-66),
- * so n must be <= 2^32-1 (the reference asserts the same, src/table.rs:380).
+ * Suffix indices are byte offsets stored as u32 (reference: src/table.rs:64-66).
+ * The reference accepts n <= 2^32-1 (src/table.rs:380); this library accepts
+ * n <= B200SA_MAX_N = 2^32-4096 (grid index arithmetic is done in u32 with
+ * tile-sized slack) and returns B200SA_ERR_TOO_LARGE above that.  Measured up
+ * to n = 3*10^9 (profiles/r01_big_configs.jsonl).
  */
 #ifndef B200SA_H
 #define B200SA_H
@@ -29,10 +32,12 @@ extern "C" {
 
 typedef struct b200sa_ctx b200sa_ctx;
 
+#define B200SA_MAX_N 0xFFFFF000ull
+
 enum {
     B200SA_OK            =  0,
     B200SA_ERR_BAD_ARG   = -1,  /* null pointer / bad size                        */
-    B200SA_ERR_TOO_LARGE = -2,  /* n > 2^32-1: reference panics, src/table.rs:380 */
+    B200SA_ERR_TOO_LARGE = -2,  /* n > B200SA_MAX_N (reference panics above 2^32-1, src/table.rs:380) */
     B200SA_ERR_NO_DEVICE = -3,
     B200SA_ERR_OOM       = -4,
     B200SA_ERR_CUDA      = -5,

@@ -456,7 +456,7 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     c->stats.sm_count = c->sm_count;
     c->stats.induce_blocks = c->induce_blocks;   // updated after classification
     c->last_n = n; c->last_m = 0;
-    if (n > 0xFFFFFFFFull) { c->last_error = "text longer than 2^32-1 bytes"; return B200SA_ERR_TOO_LARGE; }
+    if (n > B200SA_MAX_N) { c->last_error = "text longer than 2^32-4096 bytes"; return B200SA_ERR_TOO_LARGE; }
     if (n == 0) return B200SA_OK;
     if (n == 1) { CU_TRY(c, cudaMemsetAsync(d_sa, 0, 4, c->stream)); return B200SA_OK; }
     const uint8_t *text = d_text;
@@ -570,7 +570,7 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
 
 static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint32_t *d_sa, uint32_t *d_lcp,
                    bool reuse_pack) {
-    if (n > 0xFFFFFFFFull) return B200SA_ERR_TOO_LARGE;
+    if (n > B200SA_MAX_N) return B200SA_ERR_TOO_LARGE;
     if (n == 0) return B200SA_OK;
     uint32_t n32 = (uint32_t)n;
     TRY(ensure(c, c->isa, (size_t)n * 4));
@@ -789,7 +789,7 @@ int b200sa_lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
 
 static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *sa_out, uint32_t *lcp_out,
                       const uint32_t *sa_in) {
-    if (n > 0xFFFFFFFFull) { c->last_error = "text longer than 2^32-1 bytes"; return B200SA_ERR_TOO_LARGE; }
+    if (n > B200SA_MAX_N) { c->last_error = "text longer than 2^32-4096 bytes"; return B200SA_ERR_TOO_LARGE; }
     CU_TRY(c, cudaSetDevice(c->device));
     begin_call(c, nullptr);
     memset(&c->stats, 0, sizeof c->stats);
@@ -844,7 +844,7 @@ int b200sa_positions_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const
                          const uint8_t *d_queries, const uint64_t *d_q_off, uint32_t nq, uint32_t *d_start,
                          uint32_t *d_end, void *stream) {
     if (!c || (nq > 0 && (!d_q_off || !d_start || !d_end)) || (n > 0 && (!d_text || !d_sa))) return B200SA_ERR_BAD_ARG;
-    if (n > 0xFFFFFFFFull) return B200SA_ERR_TOO_LARGE;
+    if (n > B200SA_MAX_N) return B200SA_ERR_TOO_LARGE;
     CU_TRY(c, cudaSetDevice(c->device));
     begin_call(c, stream);
     if (nq > 0) {
@@ -856,7 +856,7 @@ int b200sa_positions_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const
 
 // ------------------------------------------------------------ multi-GPU shards
 int b200sa_shard_summary(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, int next_char, int *state_out, void *stream) {
-    if (!c || !d_shard || len < 1 || len > 0xFFFFFFFFull || !state_out || next_char > 255) return B200SA_ERR_BAD_ARG;
+    if (!c || !d_shard || len < 1 || len > B200SA_MAX_N || !state_out || next_char > 255) return B200SA_ERR_BAD_ARG;
     if (((uintptr_t)d_shard & 15) != 0) { c->last_error = "shard pointer must be 16-byte aligned"; return B200SA_ERR_BAD_ARG; }
     CU_TRY(c, cudaSetDevice(c->device));
     begin_call(c, stream);
@@ -880,7 +880,7 @@ int b200sa_shard_summary(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, in
 int b200sa_shard_classify(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, int prev_char, int next_char,
                           int tail_carry, uint32_t *d_stype_words, uint32_t *d_lms_words, uint32_t *d_lmspos,
                           uint64_t cap_lms, uint64_t *hist768, uint64_t *m_out, void *stream) {
-    if (!c || !d_shard || len < 1 || len > 0xFFFFFFFFull || prev_char > 255 || next_char > 255) return B200SA_ERR_BAD_ARG;
+    if (!c || !d_shard || len < 1 || len > B200SA_MAX_N || prev_char > 255 || next_char > 255) return B200SA_ERR_BAD_ARG;
     if (next_char >= 0 && tail_carry != (int)ST_L && tail_carry != (int)ST_S) return B200SA_ERR_BAD_ARG;
     if (((uintptr_t)d_shard & 15) != 0) { c->last_error = "shard pointer must be 16-byte aligned"; return B200SA_ERR_BAD_ARG; }
     CU_TRY(c, cudaSetDevice(c->device));
@@ -910,7 +910,7 @@ int b200sa_shard_classify(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, i
 // ------------------------------------------------------------ test hooks
 int b200sa_test_classify(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *stype_words, uint32_t *lms_words,
                          uint32_t *hist768, uint32_t *lmspos, uint64_t cap_lms, uint64_t *m_out) {
-    if (!c || !text || n < 1 || n > 0xFFFFFFFFull) return B200SA_ERR_BAD_ARG;
+    if (!c || !text || n < 1 || n > B200SA_MAX_N) return B200SA_ERR_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
     begin_call(c, nullptr);
     TRY(ensure(c, c->text, n));

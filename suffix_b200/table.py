@@ -33,7 +33,7 @@ class SuffixTable:
         if _table is not None:
             self._table = _table
             return
-        if len(self._text) > 0xFFFFFFFF:
+        if len(self._text) > 0xFFFFF000:   # B200SA_MAX_N
             raise OverflowError("text longer than 2^32-1 bytes")
         t = np.frombuffer(self._text, dtype=np.uint8)
         with _lock:                           # default context is not thread-safe

@@ -122,9 +122,12 @@ def lms_equal(T, S, lms, a, b):
     return False
 
 
-def doubling_sa(R):
-    """Suffix array of the reduced string by rank-pair doubling with
-    group-start ranks; only non-singleton groups stay active."""
+def doubling_sa(R, kgram=None):
+    """Suffix array of the reduced string by iterated rank/rename with
+    group-start ranks; only non-singleton groups stay active.  The first
+    refinement sorts by a k-gram of dense names (depth 1 -> k), later rounds by
+    (group, rank[i+h]) pairs with h doubling -- the device's scheme
+    (DESIGN.md 2.2); kgram=None picks k = floor(64 / bits(names+1)) like the device."""
     m = len(R)
     sa = sorted(range(m), key=lambda i: R[i])              # stable radix sort by name
     rank = [0] * m
@@ -142,9 +145,16 @@ def doubling_sa(R):
     agrp = [grp[p] for p in act]
     h = 1
     rounds = 0
+    if kgram is None:
+        bw = max(1, (max(R) + 1).bit_length()) if m else 1
+        kgram = min(8, 64 // bw)
     while apos:
         rounds += 1
-        keys = [(agrp[k], rank[asuf[k] + h] if asuf[k] + h < m else 0) for k in range(len(apos))]
+        first = rounds == 1 and kgram >= 2
+        if first:
+            keys = [tuple((R[asuf[k] + j] + 1) if asuf[k] + j < m else 0 for j in range(kgram)) for k in range(len(apos))]
+        else:
+            keys = [(agrp[k], rank[asuf[k] + h] if asuf[k] + h < m else 0) for k in range(len(apos))]
         order = sorted(range(len(apos)), key=lambda k: keys[k])
         skeys = [keys[k] for k in order]
         ssuf = [asuf[k] for k in order]
@@ -158,7 +168,7 @@ def doubling_sa(R):
         apos = [apos[k] for k in keep]
         asuf = [ssuf[k] for k in keep]
         agrp = [ngrp[k] for k in keep]
-        h *= 2
+        h = kgram if first else h * 2
     return sa, rounds
 
 

@@ -56,3 +56,8 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower() or f == "gen.py", (f, "product code must not reference oracle/")
+
+
+def test_header_documents_max_n():
+    src = open(os.path.join(ROOT, "include", "b200sa.h")).read()
+    assert "B200SA_MAX_N 0xFFFFF000ull" in src
