@@ -136,6 +136,23 @@ class SuffixTable:
                 hi = mid
         return None
 
+    # ---- persistence: the only "wire format" the reference API implies is
+    # from_parts/into_parts (src/table.rs:111-127): text bytes + little-endian u32 table.
+    def save(self, path: str) -> None:
+        """Writes `<path>.text` (raw bytes) and `<path>.sa` (raw little-endian u32)."""
+        with open(path + ".text", "wb") as f:
+            f.write(self._text)
+        self._table.astype("<u4").tofile(path + ".sa")
+
+    @classmethod
+    def load(cls, path: str, mmap: bool = True) -> "SuffixTable":
+        """from_parts over files written by save(); the table is memory-mapped by default."""
+        with open(path + ".text", "rb") as f:
+            text = f.read()
+        table = np.memmap(path + ".sa", dtype="<u4", mode="r") if mmap else np.fromfile(path + ".sa", dtype="<u4")
+        assert len(text) == len(table), "text and table lengths differ"
+        return cls(text, _table=table)
+
     def last_stats(self) -> dict:
         return getattr(self, "_stats", {})
 

@@ -47,6 +47,13 @@ def test_kat_positions(case):
     assert (hit in case["positions"]) if case["positions"] else hit is None
 
 
+def test_save_load_roundtrip(tmp_path):
+    sa = SuffixTable("The quick brown fox was very quick.")
+    sa.save(str(tmp_path / "idx"))
+    sb = SuffixTable.load(str(tmp_path / "idx"))
+    assert sa == sb and sb.positions("quick").tolist() == [4, 29]
+
+
 def test_parts_roundtrip():
     # tests/tests.rs:171-179
     sa = SuffixTable("poëzie")
