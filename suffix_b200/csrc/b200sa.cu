@@ -980,7 +980,7 @@ int64_t b200sa_debug_fetch(b200sa_ctx *c, int which, void *out, uint64_t cap) {
         case 2: src = c->reduced.p; count = c->last_m; break;
         case 3: src = c->sa_r.p; count = c->last_m; break;
         case 4: src = c->lmslist.p; count = c->last_m; break;
-        case 5: src = c->small.p ? (const void *)(ptr<uint32_t>(c->small) + 32) : nullptr; count = 4; break;
+        case 5: src = c->small.p ? (const void *)(ptr<uint32_t>(c->small) + 32) : nullptr; count = 10; break;
         case 6: src = c->tables.p; count = T_HIST; break;
         default: return B200SA_ERR_BAD_ARG;
     }

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
     if (tid == 0) { sh.st_c = SPASS ? 255 : 0; sh.st_phase = 0; sh.st_begin = 0; sh.streak = 0; sh.streak_c = -1; }
     __syncthreads();
     if (!SPASS && bid == 0 && tid == 0) A.sa[sh.bstart[lastc]] = A.n - 1u;
-    uint32_t bigcount = 0;
+    uint32_t bigcount = 0, smallcount = 0, bigtiles = 0;
 
     while (true) {
         if (tid == 0) induce_peek<SPASS>(A, sh);
@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
             if (bid == 0) {
                 while (sh.has && sh.seg.len <= (uint32_t)TILE) {
                     Seg g = sh.seg;
+                    smallcount++;
                     const bool chain = sh.is_chain != 0;
                     const int32_t cc = sh.ns_c;                 // a chain segment keeps ns_c == its bucket
                     __syncthreads();
@@ -443,6 +444,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
         uint32_t *cntbuf = A.blk_cnt + (size_t)(bigcount & 1u) * G * 256u;
         bigcount++;
         uint32_t tiles = (g.len + TILE - 1) / TILE;
+        bigtiles += tiles;
         uint32_t tpb = (tiles + G - 1) / G;
         uint32_t nact = (tiles + tpb - 1) / tpb;
         uint32_t tb0 = bid * tpb, tb1 = tb0 + tpb;
@@ -500,6 +502,9 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
         }
         if (tid == 0) { sh.st_c = sh.ns_c; sh.st_phase = sh.ns_phase; sh.st_begin = sh.ns_begin; }
         grid.sync();
+    }
+    if (bid == 0 && tid == 0) {     // step statistics of this launch (diagnostics, tools/induce_steps.py)
+        A.err[4 + (SPASS ? 3 : 0)] = bigcount; A.err[5 + (SPASS ? 3 : 0)] = smallcount; A.err[6 + (SPASS ? 3 : 0)] = bigtiles;
     }
 }
 
