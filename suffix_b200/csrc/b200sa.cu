@@ -37,7 +37,8 @@ struct b200sa_ctx {
     cudaEvent_t ev_sa = nullptr;
     int sm_count = 0;
     int induce_blocks = 0;          // largest co-resident grid (workspace is sized for it)
-    int induce_bps_max = 1;         // occupancy bound, blocks per SM
+    int induce_bps_max = 1;         // occupancy bound over all variants, blocks per SM
+    int induce_occ[3] = {1, 1, 1};  // occupancy bound per text packing (2, 4, 8 bits)
     int induce_bps_env = 0;         // B200SA_INDUCE_BPS override (0 = adaptive)
     int cur_induce_blocks = 0;      // grid of the current build
     std::string last_error;
@@ -264,6 +265,7 @@ static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asu
         TRY(ensure(c, c->k64b, (size_t)na * 8));
     }
     int b2 = bit_length(m);
+    bool try_local = getenv("B200SA_NO_LOCAL_SORT") == nullptr;
     static const char *kSortNames[] = {"rsa_sort1", "rsa_sort2", "rsa_sort3", "rsa_sort4", "rsa_sort5", "rsa_sortN"};
     static const char *kScanNames[] = {"rsa_scan1", "rsa_scan2", "rsa_scan3", "rsa_scan4", "rsa_scan5", "rsa_scanN"};
     while (na > 0) {
@@ -280,8 +282,16 @@ static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asu
         } else {
             LAUNCH(c, k_pair_keys, cdiv(na, BLK), agrp, asuf, rank, na, m, hh, (uint32_t)b2, KA);
         }
-        uint32_t *Vsorted;
-        TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, bits, &K2, &Vsorted));
+        uint32_t *Vsorted = nullptr;
+        bool sorted_locally = false;
+        if (!first && try_local) {              // tiny groups: rank inside the group by counting
+            CU_TRY(c, cudaMemsetAsync(d_na + 24, 0, 4, c->stream));
+            LAUNCH(c, k_group_local_sort, cdiv(na, BLK), KA, asuf, na, (uint32_t)b2, KB, ascratch, d_na + 24);
+            TRY(read_words(c, d_na + 24, 1));
+            if (c->h_pin[0] == 0) { K2 = KB; Vsorted = ascratch; sorted_locally = true; }
+            else try_local = false;             // some group is large: radix sort from now on
+        }
+        if (!sorted_locally) TRY(sort_pairs<uint64_t>(c, KA, asuf, KB, ascratch, na, bits, &K2, &Vsorted));
         uint32_t *Vother = (Vsorted == asuf) ? ascratch : asuf;
         { uint32_t ri = rounds - *rounds_io; TRY(mark(c, kScanNames[ri <= 5 ? ri - 1 : 5])); }
         TRY((dev_scan<OpMaxSum>(c, InGroupActive<uint64_t>{K2, apos, na},
@@ -438,7 +448,9 @@ static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t
         // per SM; many buckets -> grid-sync bound -> one block per SM
         int bps = sigma <= 16 ? 3 : (sigma <= 64 ? 2 : 1);
         if (c->induce_bps_env) bps = c->induce_bps_env;
-        if (bps > c->induce_bps_max) bps = c->induce_bps_max;
+        int occ_here = c->induce_occ[c->bits == 2 ? 0 : (c->bits == 4 ? 1 : 2)];
+        if (bps > occ_here) bps = occ_here;
+        if (bps < 1) bps = 1;
         c->cur_induce_blocks = c->sm_count * bps;
     }
     TRY(ensure(c, c->lmspos, (size_t)m * 4));
@@ -712,13 +724,20 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_sa, cudaEventDisableTiming) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     if (cudaMallocHost((void **)&c->h_pin, 64 * sizeof(uint32_t)) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
-    int occ = 1 << 30;
-    for (int sp = 0; sp < 2; sp++)
-        for (int b : {2, 4, 8}) {
-            int o = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, induce_fn(sp != 0, b), BLK, 0);
-            if (o < occ) occ = o;
+    int occ = 0;
+    {
+        const int bb[3] = {2, 4, 8};
+        for (int k = 0; k < 3; k++) {
+            int ok = 1 << 30;
+            for (int sp = 0; sp < 2; sp++) {
+                int o = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, induce_fn(sp != 0, bb[k]), BLK, 0);
+                if (o < ok) ok = o;
+            }
+            c->induce_occ[k] = ok > 4 ? 4 : ok;
+            if (c->induce_occ[k] > occ) occ = c->induce_occ[k];
         }
+    }
     if (occ < 1) { cudaFreeHost(c->h_pin); delete c; return B200SA_ERR_CUDA; }
     c->induce_bps_max = occ > 4 ? 4 : occ;
     if (const char *e = getenv("B200SA_INDUCE_BPS")) { int v = atoi(e); if (v >= 1) c->induce_bps_env = v > occ ? occ : v; }

@@ -251,6 +251,40 @@ __global__ void __launch_bounds__(BLK) k_pair_keys(const uint32_t *agrp, const u
     keys[k] = ((uint64_t)agrp[k] << b2) | r2;
 }
 
+// Later refinement rounds: after the k-gram round almost every ambiguous group
+// has 2-3 members, so a global radix sort (7 passes) is overkill.  Each element
+// finds its group (run of equal high key part) by scanning its neighbours and
+// takes the rank of its key inside the group by counting -- O(g) reads, one
+// scatter.  Groups larger than GL_LIMIT raise *overflow and the caller falls
+// back to the one-sweep sort for that round.
+constexpr int GL_LIMIT = 1024;
+__global__ void __launch_bounds__(BLK) k_group_local_sort(const uint64_t *__restrict__ keys,
+                                                          const uint32_t *__restrict__ suf, uint32_t na, uint32_t b2,
+                                                          uint64_t *kout, uint32_t *sout, uint32_t *overflow) {
+    uint32_t k = blockIdx.x * BLK + threadIdx.x;
+    if (k >= na) return;
+    if (*(volatile uint32_t *)overflow) return;          // somebody already met a large group: the round is redone
+    const uint64_t mine = keys[k];
+    const uint64_t g = mine >> b2;
+    uint32_t lo = k, hi = k + 1;
+    int steps = 0;
+    while (lo > 0 && (keys[lo - 1] >> b2) == g) {
+        lo--;
+        if (++steps > GL_LIMIT || ((steps & 63) == 0 && *(volatile uint32_t *)overflow)) { *overflow = 1u; return; }
+    }
+    while (hi < na && (keys[hi] >> b2) == g) {
+        hi++;
+        if (++steps > GL_LIMIT || ((steps & 63) == 0 && *(volatile uint32_t *)overflow)) { *overflow = 1u; return; }
+    }
+    uint32_t pos = 0;
+    for (uint32_t j = lo; j < hi; j++) {
+        uint64_t o = keys[j];
+        pos += (o < mine || (o == mine && j < k)) ? 1u : 0u;
+    }
+    kout[lo + pos] = mine;
+    sout[lo + pos] = suf[k];
+}
+
 // ------------------------------------------------------------ LCP
 // Phi / PLCP formulation of Kasai (same values as the reference's
 // lcp_lens_quadratic, src/table.rs:348-361; the algorithm is the byte-level
