@@ -198,13 +198,10 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def step_dev():
-        ctx.build_dev(d_text.data_ptr(), n, d_sa.data_ptr(), sptr)
+        ctx.build_lcp_dev(d_text.data_ptr(), n, d_sa.data_ptr(), d_lcp.data_ptr(), sptr)
         ph = ctx.phase_times()
         launches = ctx.stats()["kernel_launches"]
-        ctx.lcp_dev(d_text.data_ptr(), n, d_sa.data_ptr(), d_lcp.data_ptr(), sptr)
-        ph2 = ctx.phase_times()
-        launches += ctx.stats()["kernel_launches"]
-        return ph, ph2, launches
+        return ph, [], launches
 
     # ---------------- device-resident timing (`value`)
     for _ in range(warm):

@@ -75,6 +75,10 @@ int b200sa_build_dev(b200sa_ctx *ctx, const uint8_t *d_text, uint64_t n,
                      uint32_t *d_sa, void *stream);
 int b200sa_lcp_dev(b200sa_ctx *ctx, const uint8_t *d_text, uint64_t n,
                    const uint32_t *d_sa, uint32_t *d_lcp, void *stream);
+/* new + lcp_lens in one device-resident call (the packed text of the build is
+ * reused by the LCP kernels instead of being rebuilt). */
+int b200sa_build_lcp_dev(b200sa_ctx *ctx, const uint8_t *d_text, uint64_t n,
+                         uint32_t *d_sa, uint32_t *d_lcp, void *stream);
 
 /* ---- batched queries over a device-resident index ----
  * Replaces SuffixTable::positions (src/table.rs:223-259) for a batch: query q

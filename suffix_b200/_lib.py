@@ -43,6 +43,7 @@ def lib():
         "b200sa_build_lcp": ([vp, vp, u64, vp, vp], ci),
         "b200sa_build_dev": ([vp, vp, u64, vp, vp], ci),
         "b200sa_lcp_dev": ([vp, vp, u64, vp, vp, vp], ci),
+        "b200sa_build_lcp_dev": ([vp, vp, u64, vp, vp, vp], ci),
         "b200sa_positions_dev": ([vp, vp, u64, vp, vp, vp, u32, vp, vp, vp], ci),
         "b200sa_shard_summary": ([vp, vp, u64, ci, ctypes.POINTER(ci), vp], ci),
         "b200sa_shard_classify": ([vp, vp, u64, ci, ci, ci, vp, vp, vp, u64, vp, ctypes.POINTER(u64), vp], ci),
@@ -122,6 +123,9 @@ class Context:
 
     def lcp_dev(self, d_text: int, n: int, d_sa: int, d_lcp: int, stream: int = 0):
         self._check(lib().b200sa_lcp_dev(self._h, d_text, n, d_sa, d_lcp, stream))
+
+    def build_lcp_dev(self, d_text: int, n: int, d_sa: int, d_lcp: int, stream: int = 0):
+        self._check(lib().b200sa_build_lcp_dev(self._h, d_text, n, d_sa, d_lcp, stream))
 
     def positions_dev(self, d_text, n, d_sa, d_q, d_qoff, nq, d_start, d_end, stream: int = 0):
         self._check(lib().b200sa_positions_dev(self._h, d_text, n, d_sa, d_q, d_qoff, nq, d_start, d_end, stream))

@@ -284,8 +284,16 @@ static int doubling_rounds(b200sa_ctx *c, uint32_t m, uint32_t na, uint32_t *asu
         }
         uint32_t *Vsorted = nullptr;
         bool sorted_locally = false;
-        if (!first && try_local) {              // tiny groups: rank inside the group by counting
-            CU_TRY(c, cudaMemsetAsync(d_na + 24, 0, 4, c->stream));
+        bool use_local = !first && try_local;
+        if (use_local) {                        // probe ~4096 elements: are large groups common?
+            CU_TRY(c, cudaMemsetAsync(d_na + 24, 0, 16, c->stream));   // [24] overflow, [25] large count, [26] max size
+            uint32_t stride = na / 4096u; if (stride < 1) stride = 1;
+            uint32_t samples = cdiv(na, stride);
+            LAUNCH(c, k_group_probe, cdiv(samples, BLK), KA, na, (uint32_t)b2, stride, d_na + 25);
+            TRY(read_words(c, d_na + 25, 2));
+            if (c->h_pin[0] * 20u > samples) use_local = false;   // > 5 % of the elements in big groups: this round only
+        }
+        if (use_local) {                        // tiny groups: rank inside the group by counting
             LAUNCH(c, k_group_local_sort, cdiv(na, BLK), KA, asuf, na, (uint32_t)b2, KB, ascratch, d_na + 24);
             TRY(read_words(c, d_na + 24, 1));
             if (c->h_pin[0] == 0) { K2 = KB; Vsorted = ascratch; sorted_locally = true; }
@@ -802,6 +810,26 @@ int b200sa_lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
     CU_TRY(c, cudaSetDevice(c->device));
     begin_call(c, stream);
     int rc = lcp_dev(c, d_text, n, d_sa, d_lcp, false);
+    if (rc == B200SA_OK) rc = end_call(c);
+    return rc;
+}
+
+int b200sa_build_lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint32_t *d_lcp,
+                         void *stream) {
+    if (!c || (n > 0 && (!d_text || !d_sa || !d_lcp))) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    int rc = build_dev(c, d_text, n, d_sa);
+    if (rc == B200SA_OK) {
+        // build_dev may have classified an aligned copy of the text; the packed text (or that
+        // copy) is still valid, so the LCP kernels reuse it (n >= 2 means classification ran)
+        const uint8_t *t = (((uintptr_t)d_text & 15) != 0 && n >= 2) ? ptr<uint8_t>(c->text) : d_text;
+        uint32_t launches = c->launches;
+        b200sa_stats st = c->stats;
+        rc = lcp_dev(c, t, n, d_sa, d_lcp, n >= 2);
+        c->stats = st;
+        (void)launches;
+    }
     if (rc == B200SA_OK) rc = end_call(c);
     return rc;
 }

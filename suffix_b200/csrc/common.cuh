@@ -236,6 +236,21 @@ __device__ __forceinline__ void hist_add_private(uint32_t *s_warp_hist, uint32_t
     __syncwarp();
 }
 
+// Ballot-built peer mask variant for near-random 8-bit digits (radix-sort
+// histograms): fixed 9 ballots instead of a MATCH that iterates over up to 32
+// distinct values.
+__device__ __forceinline__ void hist_add_private_ballot(uint32_t *s_warp_hist, uint32_t key, bool valid) {
+    uint32_t peers = __ballot_sync(FULL, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        bool bit = (key >> b) & 1u;
+        uint32_t bal = __ballot_sync(FULL, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    if (valid && (peers & lanemask_lt()) == 0) s_warp_hist[key] += (uint32_t)__popc(peers);
+    __syncwarp();
+}
+
 // ------------------------------------------------------------ radix passes
 // One stable LSD pass over N items whose 8-bit digit is DigF(i); MoveF(i,dst)
 // moves item i to output slot dst.  Block b owns tiles [b*tpb, (b+1)*tpb).
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(BLK) k_os_hist(KeyF keyf, uint64_t n, int npas
         bool valid = i < n;
         K key = valid ? keyf(i) : (K)0;
         for (int p = 0; p < npass; p++)
-            hist_add_private(mine + p * 256, (uint32_t)(key >> (shift0 + 8 * p)) & 0xffu, valid);
+            hist_add_private_ballot(mine + p * 256, (uint32_t)(key >> (shift0 + 8 * p)) & 0xffu, valid);
     }
     __syncthreads();
     for (int p = 0; p < npass; p++) {

@@ -257,24 +257,38 @@ __global__ void __launch_bounds__(BLK) k_pair_keys(const uint32_t *agrp, const u
 // takes the rank of its key inside the group by counting -- O(g) reads, one
 // scatter.  Groups larger than GL_LIMIT raise *overflow and the caller falls
 // back to the one-sweep sort for that round.
+// Probe: group sizes (capped at 128) of ~4096 evenly spaced elements; stats[0] =
+// how many of them sit in groups of >= 128.  The host skips the local sort when
+// such groups are common (each of their members would scan the whole group).
+__global__ void __launch_bounds__(BLK) k_group_probe(const uint64_t *__restrict__ keys, uint32_t na, uint32_t b2,
+                                                     uint32_t stride, uint32_t *stats) {
+    uint64_t kk = (uint64_t)(blockIdx.x * BLK + threadIdx.x) * stride;
+    if (kk >= na) return;
+    uint32_t k = (uint32_t)kk;
+    const uint64_t g = keys[k] >> b2;
+    uint32_t lo = k, hi = k + 1, size = 1;
+    while (lo > 0 && size < 128u && (keys[lo - 1] >> b2) == g) { lo--; size++; }
+    while (hi < na && size < 128u && (keys[hi] >> b2) == g) { hi++; size++; }
+    if (size >= 128u) atomicAdd(&stats[0], 1u);      // member of a group of >= 128
+    atomicMax(&stats[1], size);
+}
 constexpr int GL_LIMIT = 1024;
 __global__ void __launch_bounds__(BLK) k_group_local_sort(const uint64_t *__restrict__ keys,
                                                           const uint32_t *__restrict__ suf, uint32_t na, uint32_t b2,
                                                           uint64_t *kout, uint32_t *sout, uint32_t *overflow) {
     uint32_t k = blockIdx.x * BLK + threadIdx.x;
     if (k >= na) return;
-    if (*(volatile uint32_t *)overflow) return;          // somebody already met a large group: the round is redone
     const uint64_t mine = keys[k];
     const uint64_t g = mine >> b2;
     uint32_t lo = k, hi = k + 1;
     int steps = 0;
     while (lo > 0 && (keys[lo - 1] >> b2) == g) {
         lo--;
-        if (++steps > GL_LIMIT || ((steps & 63) == 0 && *(volatile uint32_t *)overflow)) { *overflow = 1u; return; }
+        if (++steps > GL_LIMIT) { *overflow = 1u; return; }
     }
     while (hi < na && (keys[hi] >> b2) == g) {
         hi++;
-        if (++steps > GL_LIMIT || ((steps & 63) == 0 && *(volatile uint32_t *)overflow)) { *overflow = 1u; return; }
+        if (++steps > GL_LIMIT) { *overflow = 1u; return; }
     }
     uint32_t pos = 0;
     for (uint32_t j = lo; j < hi; j++) {

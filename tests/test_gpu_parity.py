@@ -252,8 +252,18 @@ def test_build_dev_matches_host(ctx):
     want = oracle.sais(t)
     assert np.array_equal(d_sa.cpu().numpy().view(np.uint32), want)
     assert np.array_equal(d_lcp.cpu().numpy().view(np.uint32), oracle.lcp_kasai(t, want))
+    d_sa.zero_(); d_lcp.zero_()
+    ctx.build_lcp_dev(d_t.data_ptr(), len(t), d_sa.data_ptr(), d_lcp.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sa.cpu().numpy().view(np.uint32), want)
+    assert np.array_equal(d_lcp.cpu().numpy().view(np.uint32), oracle.lcp_kasai(t, want))
     # unaligned device pointer (exercises the internal aligned copy)
     d_t2 = torch.from_numpy(np.concatenate([[0], t]).astype(np.uint8)).to(dev)[1:]
     ctx.build_dev(d_t2.data_ptr(), len(t), d_sa.data_ptr(), stream)
     torch.cuda.synchronize()
     assert np.array_equal(d_sa.cpu().numpy().view(np.uint32), want)
+    d_sa.zero_(); d_lcp.zero_()
+    ctx.build_lcp_dev(d_t2.data_ptr(), len(t), d_sa.data_ptr(), d_lcp.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_sa.cpu().numpy().view(np.uint32), want)
+    assert np.array_equal(d_lcp.cpu().numpy().view(np.uint32), oracle.lcp_kasai(t, want))
