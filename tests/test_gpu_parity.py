@@ -267,3 +267,44 @@ def test_build_dev_matches_host(ctx):
     torch.cuda.synchronize()
     assert np.array_equal(d_sa.cpu().numpy().view(np.uint32), want)
     assert np.array_equal(d_lcp.cpu().numpy().view(np.uint32), oracle.lcp_kasai(t, want))
+
+
+def test_error_codes(ctx):
+    """Boundary error behaviour (include/b200sa.h): bad arguments and the size limit."""
+    L = _lib.lib()
+    buf = np.zeros(4, dtype=np.uint32)
+    t = np.frombuffer(b"abcd", dtype=np.uint8)
+    assert L.b200sa_build(ctx._h, None, 4, buf.ctypes.data) == -1                 # B200SA_ERR_BAD_ARG
+    assert L.b200sa_build(ctx._h, t.ctypes.data, 4, None) == -1
+    assert L.b200sa_build(None, t.ctypes.data, 4, buf.ctypes.data) == -1
+    assert L.b200sa_build(ctx._h, t.ctypes.data, 0xFFFFF001, buf.ctypes.data) == -2  # B200SA_ERR_TOO_LARGE, nothing touched
+    assert b"2^32" in L.b200sa_last_error(ctx._h)
+    assert L.b200sa_build(ctx._h, None, 0, None) == 0                              # empty text: no launch
+    assert ctx.stats()["kernel_launches"] == 0
+    one = np.zeros(1, dtype=np.uint32) + 7
+    assert L.b200sa_build(ctx._h, t.ctypes.data, 1, one.ctypes.data) == 0 and one[0] == 0
+
+
+def test_two_contexts_two_threads():
+    """Distinct contexts are independent: two host threads,
+    two contexts on the same device, interleaved builds."""
+    import threading
+    texts = [gen.dna(400_000, seed=11), gen.rand_bytes(300_000, seed=12)]
+    want = [oracle.sais(t) for t in texts]
+    errs = []
+
+    def work(k):
+        try:
+            c = _lib.Context(0)
+            for _ in range(5):
+                sa, lcp = c.build_lcp(texts[k])
+                assert np.array_equal(sa, want[k])
+                assert np.array_equal(lcp, oracle.lcp_kasai(texts[k], want[k]))
+            c.close()
+        except Exception as e:          # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
