@@ -163,7 +163,7 @@ def run_reference(args):
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    _emit(json.dumps(out))
     return 0
 
 
@@ -328,13 +328,31 @@ def run_gpu(args):
             "levels": {"n": n, "m": stats["m"], "names": stats["names"], "doubling_rounds": stats["doubling_rounds"]},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line: str):
+    """The contract is ONE JSON line on stdout: everything else any library prints
+    (NCCL banners etc.) is diverted to stderr by main(); this writes to the real stdout."""
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(line + "\n")
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # fd 1 -> stderr for the duration of the run
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
