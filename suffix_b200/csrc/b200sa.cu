@@ -56,7 +56,7 @@ struct b200sa_ctx {
     DevBuf text, sa, lcp;                      // staging for the host API
     DevBuf pred, stype, lmsb, lmsrank, lmspos, lmslist, lmspred, sorted, flag, reduced, sa_r;
     DevBuf blkstate, carry, tables, small, scan_partial, radix_cnt, blkcnt;
-    DevBuf os_hist, os_status, phik, phiv, runscr;
+    DevBuf os_hist, os_status, phik, phiv, runscr, plcp_samp;
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
     DevBuf packed;
     int bits = 8;                    // bits per char of the packed text of the current call (2, 4 or 8 = raw)
@@ -658,10 +658,17 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
         LAUNCH(c, k_phi, cdiv(n, BLK), d_sa, n32, ptr<uint32_t>(c->isa));
     }
     TRY(mark(c, "lcp_plcp"));
-    uint32_t pg = cdiv(cdiv(n, LCP_CHUNK), BLK);
-    if (c->bits == 2) LAUNCH(c, (k_plcp<2>), pg, c->ptext, n32, ptr<uint32_t>(c->isa));
-    else if (c->bits == 4) LAUNCH(c, (k_plcp<4>), pg, c->ptext, n32, ptr<uint32_t>(c->isa));
-    else LAUNCH(c, (k_plcp<8>), pg, c->ptext, n32, ptr<uint32_t>(c->isa));
+    uint32_t nchunk = cdiv(n, LCP_CHUNK);
+    uint32_t pg = cdiv(nchunk, BLK), sg = cdiv(cdiv(nchunk, 32), BLK);
+    TRY(ensure(c, c->plcp_samp, (size_t)nchunk * 4));
+    uint32_t *samp = ptr<uint32_t>(c->plcp_samp), *phi = ptr<uint32_t>(c->isa);
+    if (c->bits == 2) LAUNCH(c, (k_plcp_samples<2>), sg, c->ptext, n32, phi, samp);
+    else if (c->bits == 4) LAUNCH(c, (k_plcp_samples<4>), sg, c->ptext, n32, phi, samp);
+    else LAUNCH(c, (k_plcp_samples<8>), sg, c->ptext, n32, phi, samp);
+    TRY(mark(c, "lcp_plcp_fill"));
+    if (c->bits == 2) LAUNCH(c, (k_plcp<2>), pg, c->ptext, n32, phi, samp);
+    else if (c->bits == 4) LAUNCH(c, (k_plcp<4>), pg, c->ptext, n32, phi, samp);
+    else LAUNCH(c, (k_plcp<8>), pg, c->ptext, n32, phi, samp);
     TRY(mark(c, "lcp_gather"));
     LAUNCH(c, k_lcp_gather, cdiv(n, BLK), d_sa, ptr<uint32_t>(c->isa), n32, d_lcp);
     TRY(mark(c, "end"));
@@ -762,7 +769,7 @@ void b200sa_ctx_destroy(b200sa_ctx *c) {
     DevBuf *bufs[] = {&c->text, &c->sa, &c->lcp, &c->pred, &c->stype, &c->lmsb, &c->lmsrank, &c->lmspos, &c->lmslist,
                       &c->lmspred, &c->sorted, &c->flag, &c->reduced, &c->sa_r, &c->blkstate, &c->carry, &c->tables,
                       &c->small, &c->scan_partial, &c->radix_cnt, &c->blkcnt, &c->k32b, &c->k64a, &c->k64b, &c->v0,
-                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr};
+                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr, &c->plcp_samp};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);

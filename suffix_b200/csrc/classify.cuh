@@ -312,18 +312,85 @@ __device__ __forceinline__ uint32_t text_match(const void *__restrict__ base, ui
         while (done < limit && __ldg(t + a + done) == __ldg(t + b + done)) done++;
         return done;
     } else {
-        constexpr int CPW = 32 / (BITS == 8 ? 4 : BITS);
+        constexpr int PB = (BITS == 8 ? 4 : BITS);
+        constexpr int CPW = 32 / PB;
+        // the common case ends inside the first word
+        if (limit >= (uint32_t)CPW) {
+            uint32_t x = text_bits<PB>(base, a) ^ text_bits<PB>(base, b);
+            if (x) return (uint32_t)(__ffs(x) - 1) / PB;
+            done = CPW;
+        }
+        // long matches (runs, repeats): four words per side in flight per iteration,
+        // so the loop is not one L2 round trip per word
+        while (done + 4 * CPW <= limit) {
+            uint32_t x0 = text_bits<PB>(base, a + done) ^ text_bits<PB>(base, b + done);
+            uint32_t x1 = text_bits<PB>(base, a + done + CPW) ^ text_bits<PB>(base, b + done + CPW);
+            uint32_t x2 = text_bits<PB>(base, a + done + 2 * CPW) ^ text_bits<PB>(base, b + done + 2 * CPW);
+            uint32_t x3 = text_bits<PB>(base, a + done + 3 * CPW) ^ text_bits<PB>(base, b + done + 3 * CPW);
+            if (x0) return done + (uint32_t)(__ffs(x0) - 1) / PB;
+            if (x1) return done + CPW + (uint32_t)(__ffs(x1) - 1) / PB;
+            if (x2) return done + 2 * CPW + (uint32_t)(__ffs(x2) - 1) / PB;
+            if (x3) return done + 3 * CPW + (uint32_t)(__ffs(x3) - 1) / PB;
+            done += 4 * CPW;
+        }
         while (done < limit) {
-            uint32_t x = text_bits<(BITS == 8 ? 4 : BITS)>(base, a + done) ^ text_bits<(BITS == 8 ? 4 : BITS)>(base, b + done);
+            uint32_t x = text_bits<PB>(base, a + done) ^ text_bits<PB>(base, b + done);
             uint32_t take = limit - done < (uint32_t)CPW ? limit - done : (uint32_t)CPW;
-            uint32_t mask = take == (uint32_t)CPW ? 0xffffffffu : ((1u << (take * BITS)) - 1u);
+            uint32_t mask = take == (uint32_t)CPW ? 0xffffffffu : ((1u << (take * PB)) - 1u);
             x &= mask;
-            if (x) return done + (uint32_t)(__ffs(x) - 1) / BITS;
+            if (x) return done + (uint32_t)(__ffs(x) - 1) / PB;
             done += take;
         }
         return done;
     }
 }
+// Warp-cooperative continuation of a long match: all 32 lanes call with the SAME
+// (a, b, limit); lane l compares chars [done + l*W, done + (l+1)*W) per sweep (W =
+// four words), so one sweep covers 32*W chars with coalesced loads instead of one
+// lane walking word by word through two private cache-line streams.
+template <int BITS>
+__device__ __forceinline__ uint32_t text_match_warp(const void *__restrict__ base, uint32_t a, uint32_t b,
+                                                    uint32_t limit) {
+    const uint32_t l = lane_id();
+    if (BITS == 8) {
+        const uint8_t *t = reinterpret_cast<const uint8_t *>(base);
+        uint32_t done = 0;
+        while (done < limit) {
+            uint32_t off = done + l * 4u, first = 0xffffffffu;
+#pragma unroll
+            for (int q = 3; q >= 0; q--) {
+                uint32_t o = off + q;
+                if (o < limit && __ldg(t + a + o) != __ldg(t + b + o)) first = o;
+            }
+            uint32_t m = __ballot_sync(FULL, first != 0xffffffffu);
+            if (m) return __shfl_sync(FULL, first, __ffs(m) - 1);
+            done += 128u;
+        }
+        return limit;
+    } else {
+        constexpr int PB = (BITS == 8 ? 4 : BITS);
+        constexpr uint32_t CPW = 32 / PB, W = 4 * CPW;
+        uint32_t done = 0;
+        while (done < limit) {
+            uint32_t off = done + l * W, first = 0xffffffffu;
+#pragma unroll
+            for (int q = 3; q >= 0; q--) {
+                uint32_t o = off + q * CPW;
+                if (o < limit) {
+                    uint32_t x = text_bits<PB>(base, a + o) ^ text_bits<PB>(base, b + o);
+                    uint32_t take = limit - o < CPW ? limit - o : CPW;
+                    if (take < CPW) x &= (1u << (take * PB)) - 1u;
+                    if (x) first = o + (uint32_t)(__ffs(x) - 1) / PB;
+                }
+            }
+            uint32_t m = __ballot_sync(FULL, first != 0xffffffffu);
+            if (m) return __shfl_sync(FULL, first, __ffs(m) - 1);
+            done += 32u * W;
+        }
+        return limit;
+    }
+}
+
 // Distance from LMS position p to the next LMS position (> p), or 0 if none.
 __device__ __forceinline__ uint32_t next_lms_dist(const uint32_t *__restrict__ lmsb, uint32_t n, uint32_t p) {
     uint32_t q = p + 1;

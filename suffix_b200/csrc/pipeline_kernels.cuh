@@ -347,15 +347,61 @@ __global__ void __launch_bounds__(BLK) k_phi_apply(const uint32_t *__restrict__ 
 // One thread owns LCP_CHUNK consecutive text positions: the first starts from
 // h = 0, the rest reuse h-1.  buf holds phi on entry and plcp on exit.
 constexpr int LCP_CHUNK = 32;
+// Level 1: exact plcp at every LCP_CHUNK-th text position.  One thread walks 32
+// consecutive samples with the carry plcp[i+32] >= plcp[i]-32, so a restart from
+// h = 0 happens once per 1024 positions instead of once per 32 (inside a run or
+// repeat of length L a restart costs O(L)).
+constexpr uint32_t LCP_SOLO = 256;       // chars a lane compares alone before the warp takes over
 template <int BITS>
-__global__ void __launch_bounds__(BLK) k_plcp(const void *__restrict__ ptext, uint32_t n, uint32_t *buf) {
+__global__ void __launch_bounds__(BLK) k_plcp_samples(const void *__restrict__ ptext, uint32_t n,
+                                                      const uint32_t *__restrict__ phi, uint32_t *samp) {
+    uint64_t t = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+    uint64_t s0 = t * 32;
+    uint32_t h = 0;
+    for (int j = 0; j < 32; j++) {                       // no early exit: the warp cooperates below
+        uint64_t sidx = s0 + j, i = sidx * LCP_CHUNK;
+        bool live = i < n;
+        uint32_t jp = live ? phi[i] : PHI_NONE;
+        bool cmp = live && jp != PHI_NONE;
+        uint32_t a = 0, b = 0, limit = 0, got = 0;
+        if (cmp) {
+            a = (uint32_t)i + h; b = jp + h;
+            limit = n - (a > b ? a : b);
+            uint32_t solo = limit < LCP_SOLO ? limit : LCP_SOLO;
+            got = text_match<BITS>(ptext, a, b, solo);
+        }
+        // lanes whose match ran through the solo window: finish them one by one, warp-wide
+        uint32_t pending = __ballot_sync(FULL, cmp && got == LCP_SOLO && limit > LCP_SOLO);
+        while (pending) {
+            int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            uint32_t aa = __shfl_sync(FULL, a, src) + LCP_SOLO, bb = __shfl_sync(FULL, b, src) + LCP_SOLO;
+            uint32_t ll = __shfl_sync(FULL, limit, src) - LCP_SOLO;
+            uint32_t more = text_match_warp<BITS>(ptext, aa, bb, ll);
+            if ((int)lane_id() == src) got += more;
+        }
+        if (live) {
+            h = cmp ? h + got : 0u;
+            samp[sidx] = h;
+            h = h > (uint32_t)LCP_CHUNK ? h - LCP_CHUNK : 0u;
+        }
+    }
+}
+// Level 2: every thread owns LCP_CHUNK consecutive positions; the first one takes
+// its value from the samples, the rest reuse h-1.  buf holds phi on entry and plcp
+// on exit.
+template <int BITS>
+__global__ void __launch_bounds__(BLK) k_plcp(const void *__restrict__ ptext, uint32_t n, uint32_t *buf,
+                                              const uint32_t *__restrict__ samp) {
     uint64_t t = (uint64_t)blockIdx.x * BLK + threadIdx.x;
     uint64_t i0 = t * LCP_CHUNK;
     if (i0 >= n) return;
     uint64_t i1 = i0 + LCP_CHUNK;
     if (i1 > n) i1 = n;
-    uint32_t h = 0;
-    for (uint64_t i = i0; i < i1; i++) {
+    uint32_t h = samp[t];
+    buf[i0] = h;
+    if (h > 0) h--;
+    for (uint64_t i = i0 + 1; i < i1; i++) {
         uint32_t j = buf[i];
         if (j == PHI_NONE) { buf[i] = 0; h = 0; continue; }
         uint32_t a = (uint32_t)i + h, b = j + h;     // a, b <= n (h never exceeds the shorter suffix)
