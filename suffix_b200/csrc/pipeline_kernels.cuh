@@ -66,16 +66,35 @@ __device__ __forceinline__ bool lms_substr_equal(const void *__restrict__ ptext,
     if (la != lb) return false;
     return text_match<BITS>(ptext, a, b, la + 1) == la + 1;
 }
-// flag[i] = 1 iff sorted LMS substring i starts a new name
+// flag[i] = 1 iff sorted LMS substring i starts a new name.  Substrings longer
+// than NAME_SOLO chars (runs: poly-N, padding) are finished warp-cooperatively.
+constexpr uint32_t NAME_SOLO = 256;
 template <int BITS>
 __global__ void __launch_bounds__(BLK) k_name_flags(const void *__restrict__ ptext, uint32_t n,
                                                     const uint32_t *__restrict__ lmsb,
                                                     const uint32_t *__restrict__ sorted, uint32_t m, uint8_t *flag) {
     uint32_t i = blockIdx.x * BLK + threadIdx.x;
-    if (i >= m) return;
+    bool live = i < m;
+    uint32_t a = 0, b = 0, len = 0;      // len = chars to compare (0: already decided)
     uint8_t f = 1;
-    if (i > 0) f = lms_substr_equal<BITS>(ptext, n, lmsb, sorted[i], sorted[i - 1]) ? 0 : 1;
-    flag[i] = f;
+    if (live && i > 0) {
+        a = sorted[i]; b = sorted[i - 1];
+        uint32_t la = next_lms_dist(lmsb, n, a);
+        if (la != 0 && la == next_lms_dist(lmsb, n, b)) len = la + 1;
+    }
+    uint32_t solo = len < NAME_SOLO ? len : NAME_SOLO;
+    uint32_t got = len ? text_match<BITS>(ptext, a, b, solo) : 0u;
+    uint32_t pending = __ballot_sync(FULL, len > NAME_SOLO && got == NAME_SOLO);
+    while (pending) {
+        int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        uint32_t aa = __shfl_sync(FULL, a, src) + NAME_SOLO, bb = __shfl_sync(FULL, b, src) + NAME_SOLO;
+        uint32_t ll = __shfl_sync(FULL, len, src) - NAME_SOLO;
+        uint32_t more = text_match_warp<BITS>(ptext, aa, bb, ll);
+        if ((int)lane_id() == src) got += more;
+    }
+    if (len && got == len) f = 0;
+    if (live) flag[i] = f;
 }
 struct InFlagU8 {
     const uint8_t *f;
