@@ -419,6 +419,8 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
     uint32_t *sm = ptr<uint32_t>(c->small);
     A.g_fill = sm + 64; A.g_state = reinterpret_cast<int32_t *>(sm + 320); A.err = sm + 32;
     A.run_scratch = ptr<uint32_t>(c->runscr);
+    A.run_alive = A.run_scratch + TILE;
+    A.cmd = sm + 336;
     void *args[] = {&A};
     CU_TRY(c, cudaLaunchCooperativeKernel(induce_fn(spass, c->bits), dim3(c->cur_induce_blocks), dim3(BLK), args, 0, c->stream));
     c->launches++;
@@ -495,7 +497,7 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     TRY(ensure(c, c->lmslist, (size_t)m * 4));
     TRY(ensure(c, c->lmspred, m));
     TRY(ensure(c, c->blkcnt, (size_t)2 * c->induce_blocks * 256 * 4));
-    TRY(ensure(c, c->runscr, (size_t)TILE * 4));
+    TRY(ensure(c, c->runscr, (size_t)2 * TILE * 4));
     uint32_t *lmslist = ptr<uint32_t>(c->lmslist);
     if (m > 0) {
         TRY(ensure(c, c->sorted, (size_t)m * 4));

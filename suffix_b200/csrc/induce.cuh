@@ -43,7 +43,11 @@ struct InduceArgs {
     int32_t *g_state;        // [4]   hand-off: c, phase, begin
     uint32_t *err;           // [4]   err[0] != 0 => invariant violated
     uint32_t *run_scratch;   // [TILE] run-skipping: terminal entries in scan order
+    uint32_t *run_alive;     // [TILE] run-skipping: alive entries of the epoch being emitted grid-wide
+    uint32_t *cmd;           // [8]    block 0 -> grid: {cmd, a, t_prev, rounds, base pos, bucket}
 };
+enum { CMD_NONE = 0, CMD_EMIT = 1, CMD_DONE = 2 };
+constexpr uint64_t EMIT_GRID_MIN = 32768;   // epochs with at least this many entries are emitted by the whole grid
 
 struct Seg {
     const uint32_t *src;
@@ -257,8 +261,24 @@ __device__ __noinline__ uint32_t run_left_coop(const uint8_t *__restrict__ text,
     }
 }
 
+// Emission share of one block for an epoch published in A.cmd (all blocks call it
+// between two grid syncs): rounds t_prev+1 .. t_prev+rounds, `a` alive entries each.
+template <bool SPASS>
+__device__ __forceinline__ void grid_emit(const InduceArgs &A, const IndShared &sh) {
+    const uint32_t a = __ldcg(A.cmd + 1), t_prev = __ldcg(A.cmd + 2), rounds = __ldcg(A.cmd + 3);
+    const uint32_t basepos = __ldcg(A.cmd + 4), c = __ldcg(A.cmd + 5);
+    const uint64_t items = (uint64_t)rounds * a;
+    for (uint64_t idx = (uint64_t)blockIdx.x * BLK + threadIdx.x; idx < items; idx += (uint64_t)gridDim.x * BLK) {
+        uint32_t r_off = (uint32_t)(idx / a), jj = (uint32_t)(idx % a);
+        uint32_t pos = basepos + (uint32_t)idx;
+        uint32_t slot = SPASS ? (sh.bstart[c + 1] - 1u - pos) : (sh.bstart[c] + pos);
+        A.sa[slot] = __ldcg(A.run_alive + jj) - (t_prev + 1u + r_off);
+    }
+}
+
 template <bool SPASS, int BITS>
-__device__ __noinline__ void induce_run_skip(const InduceArgs &A, IndShared &sh, const Seg &g, uint32_t c) {
+__device__ __noinline__ void induce_run_skip(const InduceArgs &A, IndShared &sh, const Seg &g, uint32_t c,
+                                             cg::grid_group &grid) {
     const uint32_t tid = threadIdx.x;
     const uint32_t k = g.len;                       // <= TILE; thread t owns list items [8t, 8t+8)
     // ---- entries and locally probed run lengths
@@ -325,11 +345,24 @@ __device__ __noinline__ void induce_run_skip(const InduceArgs &A, IndShared &sh,
             }
             __syncthreads();
             uint64_t items = (uint64_t)(thr - t_prev) * a;
-            for (uint64_t idx = tid; idx < items; idx += BLK) {
-                uint32_t r_off = (uint32_t)(idx / a), jj = (uint32_t)(idx % a);
-                uint32_t pos = F + (uint32_t)(O + idx);
-                uint32_t slot = SPASS ? (sh.bstart[c + 1] - 1u - pos) : (sh.bstart[c] + pos);
-                A.sa[slot] = sh.alive[jj] - (t_prev + 1u + r_off);
+            if (items >= EMIT_GRID_MIN) {
+                // big epoch (long runs): publish it and let the whole grid emit
+                for (uint32_t q = tid; q < a; q += BLK) A.run_alive[q] = sh.alive[q];
+                if (tid == 0) {
+                    A.cmd[1] = a; A.cmd[2] = t_prev; A.cmd[3] = thr - t_prev; A.cmd[4] = F + (uint32_t)O; A.cmd[5] = c;
+                    A.cmd[0] = CMD_EMIT;
+                }
+                __threadfence();
+                grid.sync();
+                grid_emit<SPASS>(A, sh);
+                grid.sync();
+            } else {
+                for (uint64_t idx = tid; idx < items; idx += BLK) {
+                    uint32_t r_off = (uint32_t)(idx / a), jj = (uint32_t)(idx % a);
+                    uint32_t pos = F + (uint32_t)(O + idx);
+                    uint32_t slot = SPASS ? (sh.bstart[c + 1] - 1u - pos) : (sh.bstart[c] + pos);
+                    A.sa[slot] = sh.alive[jj] - (t_prev + 1u + r_off);
+                }
             }
             O += items;
         }
@@ -409,7 +442,7 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
                     }
                     __syncthreads();
                     if (chain && sh.streak >= RUN_STREAK) {
-                        induce_run_skip<SPASS, BITS>(A, sh, g, (uint32_t)cc);
+                        induce_run_skip<SPASS, BITS>(A, sh, g, (uint32_t)cc, grid);
                         if (tid == 0) { sh.st_c = cc; sh.st_phase = 0; sh.st_begin = sh.fill[cc]; sh.streak = 0; sh.streak_c = -1; }
                         __syncthreads();
                         if (tid == 0) induce_peek<SPASS>(A, sh);
@@ -426,9 +459,21 @@ __global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
                     __syncthreads();
                 }
                 A.g_fill[tid] = sh.fill[tid];
-                if (tid == 0) { A.g_state[0] = sh.st_c; A.g_state[1] = sh.st_phase; A.g_state[2] = (int32_t)sh.st_begin; }
+                if (tid == 0) {
+                    A.g_state[0] = sh.st_c; A.g_state[1] = sh.st_phase; A.g_state[2] = (int32_t)sh.st_begin;
+                    A.cmd[0] = CMD_DONE;
+                }
+                __threadfence();
+                grid.sync();
+            } else {
+                // wait for block 0; serve grid-wide emission requests of its run skipping meanwhile
+                while (true) {
+                    grid.sync();
+                    if (__ldcg(A.cmd + 0) != CMD_EMIT) break;
+                    grid_emit<SPASS>(A, sh);
+                    grid.sync();
+                }
             }
-            grid.sync();
             if (bid != 0) {
                 sh.fill[tid] = __ldcg(A.g_fill + tid);
                 if (tid == 0) {
