@@ -51,6 +51,9 @@ struct b200sa_ctx {
     b200sa_stats stats;
     uint32_t launches = 0;
     uint32_t *h_pin = nullptr;       // pinned read-back area (64 words)
+    uint32_t *h_tab = nullptr;       // pinned copy of bstart[257] | Lcnt[256] (early SA copy-out)
+    uint32_t *early_sa_out = nullptr;   // host SA buffer of the current host-API call (or null)
+    bool early_done = false;
     size_t ws_bytes = 0;
     // ---- workspace
     DevBuf text, sa, lcp;                      // staging for the host API
@@ -59,6 +62,7 @@ struct b200sa_ctx {
     DevBuf os_hist, os_status, phik, phiv, runscr, plcp_samp;
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
     DevBuf packed;
+    uint32_t sigma = 256;            // distinct bytes of the current text
     int bits = 8;                    // bits per char of the packed text of the current call (2, 4 or 8 = raw)
     const void *ptext = nullptr;     // packed words, or the byte text when bits == 8
     uint64_t last_n = 0, last_m = 0;
@@ -388,6 +392,7 @@ static int pack_text(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t si
     uint32_t *tab = ptr<uint32_t>(c->tables);
     c->bits = 8;
     c->ptext = text;
+    c->sigma = sigma;
     if (getenv("B200SA_NOPACK")) return B200SA_OK;
     if (sigma <= 4) c->bits = 2; else if (sigma <= 16) c->bits = 4; else return B200SA_OK;
     uint32_t cpw = 32 / c->bits;
@@ -451,6 +456,8 @@ static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t
            tab + T_ALPHA, sm + 3);
     CU_TRY(c, cudaGetLastError());
     TRY((dev_scan<OpSum>(c, InPopcWords{ptr<uint32_t>(c->lmsb)}, OutStoreExcl{ptr<uint32_t>(c->lmsrank)}, nw, sm)));
+    if (c->early_sa_out)    // bucket layout for the early SA copy-out (same synchronisation as the read below)
+        CU_TRY(c, cudaMemcpyAsync(c->h_tab, tab + T_BSTART, 513 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     TRY(read_words(c, sm, 4));
     uint32_t m = c->h_pin[0], sigma = c->h_pin[3];
     TRY(pack_text(c, text, n, sigma));
@@ -469,6 +476,24 @@ static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t
         CU_TRY(c, cudaGetLastError());
     }
     *m_out = m;
+    return B200SA_OK;
+}
+
+// Host API only: the L parts of all buckets are final after the last L pass and the
+// S parts after the last S pass, so the SA can start leaving over PCIe one S-pass
+// early (few buckets only: one memcpy per bucket part).
+static int early_copy_parts(b200sa_ctx *c, const uint32_t *d_sa, bool s_parts) {
+    if (!c->early_sa_out || c->sigma > 16) return B200SA_OK;
+    CU_TRY(c, cudaEventRecord(c->ev_sa, c->stream));
+    CU_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_sa, 0));
+    const uint32_t *bstart = c->h_tab, *Lcnt = c->h_tab + 257;
+    for (int b = 0; b < 256; b++) {
+        uint32_t lo = bstart[b] + (s_parts ? Lcnt[b] : 0u);
+        uint32_t hi = s_parts ? bstart[b + 1] : bstart[b] + Lcnt[b];
+        if (hi > lo)
+            CU_TRY(c, cudaMemcpyAsync(c->early_sa_out + lo, d_sa + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    if (s_parts) c->early_done = true;
     return B200SA_OK;
 }
 
@@ -577,8 +602,10 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     // stage 2: final induce from the sorted LMS suffixes
     TRY(mark(c, "induce2_L"));
     TRY(launch_induce(c, false, text, n32, d_sa, lmslist, m));
+    TRY(early_copy_parts(c, d_sa, false));
     TRY(mark(c, "induce2_S"));
     TRY(launch_induce(c, true, text, n32, d_sa, lmslist, m));
+    TRY(early_copy_parts(c, d_sa, true));
     TRY(mark(c, "end"));
     TRY(read_words(c, ptr<uint32_t>(c->small) + 32, 4));
     if (c->h_pin[0] != 0) {
@@ -741,6 +768,7 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_sa, cudaEventDisableTiming) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     if (cudaMallocHost((void **)&c->h_pin, 64 * sizeof(uint32_t)) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
+    if (cudaMallocHost((void **)&c->h_tab, 513 * sizeof(uint32_t)) != cudaSuccess) { cudaFreeHost(c->h_pin); delete c; return B200SA_ERR_CUDA; }
     int occ = 0;
     {
         const int bb[3] = {2, 4, 8};
@@ -775,6 +803,7 @@ void b200sa_ctx_destroy(b200sa_ctx *c) {
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_tab) cudaFreeHost(c->h_tab);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_sa) cudaEventDestroy(c->ev_sa);
@@ -857,8 +886,22 @@ static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *
     CU_TRY(c, cudaMemcpyAsync(c->text.p, text, n, cudaMemcpyHostToDevice, c->stream));
     if (sa_in) CU_TRY(c, cudaMemcpyAsync(c->sa.p, sa_in, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     if (!sa_in) {
-        TRY(build_dev(c, ptr<uint8_t>(c->text), n, ptr<uint32_t>(c->sa)));
+        // early copy-out only into pinned memory: a D2H into pageable memory blocks the host
+        // thread, which would delay the launch of the last S pass
+        bool pinned = false;
         if (sa_out) {
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, sa_out) == cudaSuccess) pinned = (pa.type == cudaMemoryTypeHost);
+            else cudaGetLastError();
+        }
+        c->early_sa_out = (pinned && n >= 2 && !getenv("B200SA_NO_EARLY_COPY")) ? sa_out : nullptr;
+        c->early_done = false;
+        int brc = build_dev(c, ptr<uint8_t>(c->text), n, ptr<uint32_t>(c->sa));
+        c->early_sa_out = nullptr;
+        if (brc != B200SA_OK) { cudaStreamSynchronize(c->copy_stream); return brc; }
+        if (sa_out && c->early_done) {
+            TRY(mark(c, "d2h_sa"));      // already on its way on the copy stream
+        } else if (sa_out) {
             TRY(mark(c, "d2h_sa"));
             if (lcp_out) {      // the LCP kernels only read the SA: copy it out underneath them
                 CU_TRY(c, cudaEventRecord(c->ev_sa, c->stream));

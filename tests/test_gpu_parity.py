@@ -311,3 +311,23 @@ def test_two_contexts_two_threads():
     [x.start() for x in th]
     [x.join() for x in th]
     assert not errs, errs
+
+
+def test_host_api_pinned_buffers_early_copy(ctx):
+    """b200sa_build_lcp with pinned host buffers takes the early SA copy-out path
+    (bucket parts leave as soon as they are final); result must be identical."""
+    import torch
+    t = gen.dna(3_000_000, newline_tail=True)
+    want = oracle.sais(t)
+    h_t = torch.from_numpy(t.copy()).pin_memory()
+    h_sa = torch.empty(len(t), dtype=torch.int32).pin_memory()
+    h_lcp = torch.empty(len(t), dtype=torch.int32).pin_memory()
+    L = _lib.lib()
+    for _ in range(2):
+        h_sa.zero_()
+        assert L.b200sa_build_lcp(ctx._h, h_t.data_ptr(), len(t), h_sa.data_ptr(), h_lcp.data_ptr()) == 0
+        assert np.array_equal(h_sa.numpy().view(np.uint32), want)
+        assert np.array_equal(h_lcp.numpy().view(np.uint32), oracle.lcp_kasai(t, want))
+    h_sa.zero_()
+    assert L.b200sa_build(ctx._h, h_t.data_ptr(), len(t), h_sa.data_ptr()) == 0
+    assert np.array_equal(h_sa.numpy().view(np.uint32), want)
