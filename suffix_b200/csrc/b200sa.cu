@@ -175,18 +175,6 @@ static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, typename Op::T 
     return B200SA_OK;
 }
 
-template <class Op, class InF>
-static int dev_reduce(b200sa_ctx *c, InF in, uint64_t n, uint32_t *d_total) {
-    if (n == 0) { CU_TRY(c, cudaMemsetAsync(d_total, 0, 4, c->stream)); return B200SA_OK; }
-    uint32_t nb = cdiv(n, SCAN_CHUNK);
-    TRY(ensure(c, c->scan_partial, (size_t)nb * 4));
-    uint32_t *part = ptr<uint32_t>(c->scan_partial);
-    LAUNCH(c, (k_scan_reduce<Op, InF>), nb, in, n, part);
-    LAUNCH(c, (k_scan_partials<Op>), 1, part, nb, d_total);
-    CU_TRY(c, cudaGetLastError());
-    return B200SA_OK;
-}
-
 constexpr uint32_t MAX_RADIX_BLOCKS = 1184;   // 148 SMs x 8
 
 template <class DigF, class MoveF>

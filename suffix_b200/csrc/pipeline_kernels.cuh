@@ -3,10 +3,10 @@
 //   K6  compaction of sorted LMS substrings   (reference P10, src/table.rs:450-463)
 //   K7  naming by neighbour equality          (reference P11, src/table.rs:465-482, wstring_equal :802-820)
 //   K8  reduced string in text order          (reference P12, src/table.rs:484-492)
-//   K9  base-case inversion                   (reference P13, src/table.rs:501-506)
+//   K9  base case (unique names)              (reference P13, src/table.rs:501-506) -- no kernel needed
 //   K10 un-rename ranks -> text positions     (reference P15-P16, src/table.rs:512-530)
-//   rank-pair doubling on the reduced string  (stands in for the recursion at src/table.rs:499)
-//   K12/K13 inverse SA + Kasai-style LCP      (reference semantics src/table.rs:348-361)
+//   k-gram sort + rank-pair doubling on the reduced string (stands in for the recursion at src/table.rs:499)
+//   K12/K13 LCP: direct per-pair fast path, Phi / two-level PLCP linear path (reference semantics src/table.rs:348-361)
 //   batched positions()                       (reference src/table.rs:223-259)
 #pragma once
 #include "classify.cuh"
@@ -57,15 +57,6 @@ struct MoveU32 {
 // positions are Valleys in both, and a length mismatch shows up in the
 // reference as a type mismatch at the shorter one's last position.  A substring
 // that runs off the text (no later Valley) equals nothing (:814-819).
-template <int BITS>
-__device__ __forceinline__ bool lms_substr_equal(const void *__restrict__ ptext, uint32_t n,
-                                                 const uint32_t *__restrict__ lmsb, uint32_t a, uint32_t b) {
-    uint32_t la = next_lms_dist(lmsb, n, a);
-    if (la == 0) return false;
-    uint32_t lb = next_lms_dist(lmsb, n, b);
-    if (la != lb) return false;
-    return text_match<BITS>(ptext, a, b, la + 1) == la + 1;
-}
 // flag[i] = 1 iff sorted LMS substring i starts a new name.  Substrings longer
 // than NAME_SOLO chars (runs: poly-N, padding) are finished warp-cooperatively.
 constexpr uint32_t NAME_SOLO = 256;
@@ -131,11 +122,8 @@ struct OutInitFromSorted {
         if (single || write_all) rank[tr] = g + 1u;
     }
 };
-// K9: all names unique -> SA of the reduced string is the inverse permutation
-__global__ void __launch_bounds__(BLK) k_invert_perm(const uint32_t *reduced, uint32_t m, uint32_t *sa_r) {
-    uint32_t k = blockIdx.x * BLK + threadIdx.x;
-    if (k < m) sa_r[reduced[k]] = k;
-}
+// K9 (all names unique): the sorted LMS substrings already are the reduced SA -- OutInitFromSorted
+// writes sa_r[i] = text_rank(sorted[i]); no inversion kernel is needed (reference :501-506).
 // K10: sorted LMS suffixes = lmspos[sa_r[i]]
 __global__ void __launch_bounds__(BLK) k_unrename(const uint32_t *sa_r, const uint32_t *lmspos, uint32_t m,
                                                   uint32_t *out) {
