@@ -403,8 +403,11 @@ __device__ __noinline__ void induce_run_skip(const InduceArgs &A, IndShared &sh,
     __syncthreads();
 }
 
+#ifndef INDUCE_MINB
+#define INDUCE_MINB 2
+#endif
 template <bool SPASS, int BITS>
-__global__ void __launch_bounds__(BLK) k_induce(InduceArgs A) {
+__global__ void __launch_bounds__(BLK, INDUCE_MINB) k_induce(InduceArgs A) {
     __shared__ IndShared sh;
     cg::grid_group grid = cg::this_grid();
     const uint32_t G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
