@@ -108,6 +108,85 @@ def induce(T, SA, lms_list, lms_off, Lc, Sc, bstart, sigma=256, stats=None):
         stats["steps"] = stats.get("steps", 0) + steps
 
 
+def _multiround_chain(T, SA, c, begin, end, R, spass, bstart, fill):
+    """PLANNED device step (NOTES_ROUND1.md, idea a): one partition step that plays up
+    to R chain rounds of bucket c at once.  Entry e_j of the list [begin,end) with
+    l_j = min(run of c to its left, R) emits e_j - r into round r (1 <= r <= l_j) of the
+    chain region, round-major then list order; if l_j < R its terminal e_j - l_j
+    induces into bucket d = T[e_j - l_j - 1] (valid range as in a normal chain step),
+    ordered by (l_j, j).  Returns the new `begin` (first unprocessed slot)."""
+    sigma = len(fill)
+    F = fill[c]
+    def slot(d, k):
+        return bstart[d + 1] - 1 - k if spass else bstart[d] + k
+    ents = [SA[slot(c, k)] for k in range(begin, end)]
+    runs = []
+    for e in ents:
+        l = 0
+        while l < R and e - 1 - l >= 0 and T[e - 1 - l] == c:
+            l += 1
+        runs.append(l)
+    a = [sum(1 for l in runs if l >= r) for r in range(0, R + 1)]      # a[r], r >= 1
+    off = F
+    for r in range(1, R + 1):
+        k = 0
+        for e, l in zip(ents, runs):
+            if l >= r:
+                SA[slot(c, off + k)] = e - r
+                k += 1
+        off += a[r]
+    new_begin = F + sum(a[1:R])
+    fill[c] = F + sum(a[1:R + 1])
+    # terminals, ordered by (l, j)
+    order = sorted(range(len(ents)), key=lambda j: (runs[j], j))
+    cnt = {}
+    for j in order:
+        l, e = runs[j], ents[j]
+        if l == R:
+            continue                      # still inside its run: continues in the next step
+        x = e - l
+        if x == 0:
+            continue
+        d = T[x - 1]
+        ok = (d < c) if spass else (d > c)
+        if not ok:
+            continue
+        k = fill[d] + cnt.get(d, 0)
+        SA[slot(d, k)] = x - 1
+        cnt[d] = cnt.get(d, 0) + 1
+    for d, v in cnt.items():
+        fill[d] += v
+    return new_begin
+
+
+def induce_multiround(T, SA, lms_list, lms_off, Lc, Sc, bstart, R, sigma=256):
+    """induce() with the chain rounds of every bucket played R at a time."""
+    n = len(T)
+    fill = [0] * sigma
+    SA[bstart[T[n - 1]]] = n - 1
+    fill[T[n - 1]] = 1
+    for c in range(sigma):
+        if bstart[c + 1] == bstart[c]:
+            continue
+        begin = 0
+        while fill[c] > begin:
+            begin = _multiround_chain(T, SA, c, begin, fill[c], R, False, bstart, fill)
+        assert fill[c] == Lc[c]
+        if lms_off[c + 1] > lms_off[c] and c + 1 <= sigma - 1:
+            _step(T, SA, lms_list, range(lms_off[c], lms_off[c + 1]), c + 1, sigma - 1, False, bstart, fill)
+    fill = [0] * sigma
+    for c in range(sigma - 1, -1, -1):
+        if bstart[c + 1] == bstart[c]:
+            continue
+        begin = 0
+        while fill[c] > begin:
+            begin = _multiround_chain(T, SA, c, begin, fill[c], R, True, bstart, fill)
+        assert fill[c] == Sc[c]
+        if Lc[c] > 0 and c > 0:
+            top = bstart[c] + Lc[c] - 1
+            _step(T, SA, SA, range(top, bstart[c] - 1, -1), 0, c - 1, True, bstart, fill)
+
+
 def lms_equal(T, S, lms, a, b):
     """LMS-substring equality, src/table.rs:802-820 semantics."""
     n = len(T)
@@ -172,7 +251,7 @@ def doubling_sa(R, kgram=None):
     return sa, rounds
 
 
-def build_sa(T, sigma=256, stats=None):
+def build_sa(T, sigma=256, stats=None, multiround=0):
     """Whole pipeline; T is a list/bytes of ints < sigma."""
     T = list(T)
     n = len(T)
@@ -194,7 +273,10 @@ def build_sa(T, sigma=256, stats=None):
     if m > 0:
         # stage 1: LMS grouped by first char (stable counting sort, text order)
         grouped = sorted(lmspos, key=lambda p: T[p])
-        induce(T, SA, grouped, lms_off, Lc, Sc, bstart, sigma, stats)
+        if multiround:
+            induce_multiround(T, SA, grouped, lms_off, Lc, Sc, bstart, multiround, sigma)
+        else:
+            induce(T, SA, grouped, lms_off, Lc, Sc, bstart, sigma, stats)
         assert sorted(SA) == list(range(n))
         sorted_sub = [s for s in SA if lms[s]]
         # naming
@@ -222,5 +304,8 @@ def build_sa(T, sigma=256, stats=None):
     else:
         sorted_lms = []
     SA = [None] * n
-    induce(T, SA, sorted_lms, lms_off, Lc, Sc, bstart, sigma, stats)
+    if multiround:
+        induce_multiround(T, SA, sorted_lms, lms_off, Lc, Sc, bstart, multiround, sigma)
+    else:
+        induce(T, SA, sorted_lms, lms_off, Lc, Sc, bstart, sigma, stats)
     return SA
