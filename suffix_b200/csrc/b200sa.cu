@@ -664,8 +664,7 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
         uint32_t shift = nbits > 8 ? (uint32_t)(nbits - 8) : 0u;
         CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
         CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
-        uint32_t hb = tiles < 1184u ? tiles : 1184u;
-        (void)hb;   // sa is a permutation: the digit bases are known without a histogram pass
+        // sa is a permutation: the digit bases are known without a histogram pass
         LAUNCH(c, k_os_perm_base, 1u, ghist, shift, n32);
         LAUNCH(c, (k_os_pass<uint32_t, LoadArr<uint32_t>, LoadPhiPrev>), tiles, LoadArr<uint32_t>{d_sa}, LoadPhiPrev{d_sa},
                ptr<uint32_t>(c->phik), ptr<uint32_t>(c->phiv), n, shift, ghist,
@@ -850,11 +849,9 @@ int b200sa_build_lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint3
         // build_dev may have classified an aligned copy of the text; the packed text (or that
         // copy) is still valid, so the LCP kernels reuse it (n >= 2 means classification ran)
         const uint8_t *t = (((uintptr_t)d_text & 15) != 0 && n >= 2) ? ptr<uint8_t>(c->text) : d_text;
-        uint32_t launches = c->launches;
         b200sa_stats st = c->stats;
         rc = lcp_dev(c, t, n, d_sa, d_lcp, n >= 2);
         c->stats = st;
-        (void)launches;
     }
     if (rc == B200SA_OK) rc = end_call(c);
     return rc;
