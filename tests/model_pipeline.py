@@ -187,6 +187,106 @@ def induce_multiround(T, SA, lms_list, lms_off, Lc, Sc, bstart, R, sigma=256):
             _step(T, SA, SA, range(top, bstart[c] - 1, -1), 0, c - 1, True, bstart, fill)
 
 
+def induce_paircount(T, S, lms, SA, lms_list, lms_off, Lc, Sc, bstart, sigma=256):
+    """PLANNED device formulation for large alphabets (NOTES_ROUND1.md, idea c).  With the
+    (source bucket c -> destination bucket d) pair counts known from the classifier, the
+    start of every region "entries induced from part X of bucket c into bucket d" is known
+    a priori.  All LMS-sourced inductions (L pass) and all L-part-sourced inductions (S
+    pass) then are ONE upfront, fully parallel partition each, and a bucket only needs its
+    chain rounds: half the grid-synchronised steps of the per-bucket two-list scheme."""
+    n = len(T)
+    CL, CM, CS, CLS = {}, {}, {}, {}
+    for i in range(1, n):                          # the classifier would count these pairs
+        key = (T[i], T[i - 1])                     # (source bucket, destination bucket)
+        if not S[i] and not S[i - 1]:
+            CL[key] = CL.get(key, 0) + 1           # L(c) -> d   (L pass, d >= c)
+        if lms[i]:
+            CM[key] = CM.get(key, 0) + 1           # LMS(c) -> d (L pass, d > c)
+        if S[i] and S[i - 1]:
+            CS[key] = CS.get(key, 0) + 1           # S(c) -> d   (S pass, d <= c)
+        if not S[i] and S[i - 1]:
+            CLS[key] = CLS.get(key, 0) + 1         # L(c) -> d   (S pass, d < c)
+    chars = [c for c in range(sigma) if bstart[c + 1] > bstart[c]]
+
+    # ------------------------------------------------------------------ L pass
+    baseL, baseM, chain0 = {}, {}, {}
+    for d in chars:
+        off = 1 if d == T[n - 1] else 0            # the seed n-1 sits first in its bucket
+        for c in chars:
+            if c >= d:
+                break
+            baseL[(c, d)] = off; off += CL.get((c, d), 0)
+            baseM[(c, d)] = off; off += CM.get((c, d), 0)
+        chain0[d] = off
+        assert off + CL.get((d, d), 0) == Lc[d], (d, off, Lc[d])
+    SA[bstart[T[n - 1]]] = n - 1
+    cur = {}
+    # upfront: every LMS suffix induces its predecessor (independent of all buckets' state)
+    for c in chars:
+        for k in range(lms_off[c], lms_off[c + 1]):
+            s = lms_list[k]
+            d = T[s - 1]
+            SA[bstart[d] + baseM[(c, d)] + cur.get(("M", c, d), 0)] = s - 1
+            cur[("M", c, d)] = cur.get(("M", c, d), 0) + 1
+    # per bucket: chain rounds only
+    for c in chars:
+        begin, end = 0, chain0[c]
+        nxt = chain0[c]
+        while end > begin:
+            for p in range(begin, end):
+                s = SA[bstart[c] + p]
+                if s == 0:
+                    continue
+                d = T[s - 1]
+                if d == c:
+                    SA[bstart[c] + nxt] = s - 1; nxt += 1
+                elif d > c:
+                    SA[bstart[d] + baseL[(c, d)] + cur.get(("L", c, d), 0)] = s - 1
+                    cur[("L", c, d)] = cur.get(("L", c, d), 0) + 1
+            begin, end = end, nxt
+        assert nxt == Lc[c], (c, nxt, Lc[c])
+
+    # ------------------------------------------------------------------ S pass (tail-relative slots)
+    baseS, baseLS, chain0 = {}, {}, {}
+    for d in chars:
+        off = 0
+        for c in reversed(chars):
+            if c <= d:
+                break
+            baseS[(c, d)] = off; off += CS.get((c, d), 0)
+            baseLS[(c, d)] = off; off += CLS.get((c, d), 0)
+        chain0[d] = off
+        assert off + CS.get((d, d), 0) == Sc[d], (d, off, Sc[d])
+    cur = {}
+    tail = lambda d, k: bstart[d + 1] - 1 - k
+    # upfront: every L-part entry (right to left inside its bucket) induces an S-type predecessor
+    for c in chars:
+        for p in range(bstart[c] + Lc[c] - 1, bstart[c] - 1, -1):
+            s = SA[p]
+            if s == 0:
+                continue
+            d = T[s - 1]
+            if d < c:
+                SA[tail(d, baseLS[(c, d)] + cur.get(("LS", c, d), 0))] = s - 1
+                cur[("LS", c, d)] = cur.get(("LS", c, d), 0) + 1
+    for c in reversed(chars):
+        begin, end = 0, chain0[c]
+        nxt = chain0[c]
+        while end > begin:
+            for k in range(begin, end):
+                s = SA[tail(c, k)]
+                if s == 0:
+                    continue
+                d = T[s - 1]
+                if d == c:
+                    SA[tail(c, nxt)] = s - 1; nxt += 1
+                elif d < c:
+                    SA[tail(d, baseS[(c, d)] + cur.get(("S", c, d), 0))] = s - 1
+                    cur[("S", c, d)] = cur.get(("S", c, d), 0) + 1
+            begin, end = end, nxt
+        assert nxt == Sc[c], (c, nxt, Sc[c])
+
+
 def lms_equal(T, S, lms, a, b):
     """LMS-substring equality, src/table.rs:802-820 semantics."""
     n = len(T)
@@ -251,7 +351,7 @@ def doubling_sa(R, kgram=None):
     return sa, rounds
 
 
-def build_sa(T, sigma=256, stats=None, multiround=0):
+def build_sa(T, sigma=256, stats=None, multiround=0, paircount=False):
     """Whole pipeline; T is a list/bytes of ints < sigma."""
     T = list(T)
     n = len(T)
@@ -273,7 +373,9 @@ def build_sa(T, sigma=256, stats=None, multiround=0):
     if m > 0:
         # stage 1: LMS grouped by first char (stable counting sort, text order)
         grouped = sorted(lmspos, key=lambda p: T[p])
-        if multiround:
+        if paircount:
+            induce_paircount(T, S, lms, SA, grouped, lms_off, Lc, Sc, bstart, sigma)
+        elif multiround:
             induce_multiround(T, SA, grouped, lms_off, Lc, Sc, bstart, multiround, sigma)
         else:
             induce(T, SA, grouped, lms_off, Lc, Sc, bstart, sigma, stats)
@@ -304,7 +406,9 @@ def build_sa(T, sigma=256, stats=None, multiround=0):
     else:
         sorted_lms = []
     SA = [None] * n
-    if multiround:
+    if paircount:
+        induce_paircount(T, S, lms, SA, sorted_lms, lms_off, Lc, Sc, bstart, sigma)
+    elif multiround:
         induce_multiround(T, SA, sorted_lms, lms_off, Lc, Sc, bstart, multiround, sigma)
     else:
         induce(T, SA, sorted_lms, lms_off, Lc, Sc, bstart, sigma, stats)

@@ -49,3 +49,17 @@ def test_model_multiround_chain(name, data, R):
 def test_model_multiround_prop(s, R):
     t = s.encode()
     assert mp.build_sa(t, multiround=R) == oracle.naive_sa(t).tolist()
+
+
+@pytest.mark.parametrize("name,data", families.adversarial(), ids=lambda x: x if isinstance(x, str) else "")
+def test_model_paircount_induce(name, data):
+    """Groundwork for large alphabets (NOTES_ROUND1.md, idea c): with (source, destination)
+    pair counts the LMS- and L-part-sourced inductions are one upfront partition each."""
+    data = data[:4000]
+    assert mp.build_sa(data, paircount=True) == oracle.sais(data).tolist()
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.binary(max_size=100))
+def test_model_paircount_prop(t):
+    assert mp.build_sa(t, paircount=True) == oracle.naive_sa(t).tolist()
