@@ -131,40 +131,75 @@ def _oracle_time(text_np, with_lcp=True):
     from oracle import oracle          # CPU baseline leg: the one place bench.py executes oracle/
     t0 = time.perf_counter()
     sa = oracle.sais(text_np)
-    if with_lcp:
-        oracle.lcp_lens(text_np, sa)
-    return time.perf_counter() - t0, sa
+    lcp = oracle.lcp_lens(text_np, sa) if with_lcp else None
+    return time.perf_counter() - t0, sa, lcp
+
+
+def _pin_to_cpu(k):
+    """Pins the calling thread to one host core (best effort)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        os.sched_setaffinity(threading.get_native_id(), {cpus[k % len(cpus)]})
+    except Exception:
+        pass
 
 
 def run_reference(args):
+    """The reference's own CPU algorithm on the SAME config as the GPU arm: every
+    timed step indexes all N_TEXT bytes of the workload (SA + LCP).  The reference
+    is single-threaded, so one replica uses one core; at --gpus N (weak scaling:
+    N independent 100 MB texts) rank 0 runs N replicas concurrently on N pinned
+    cores, mirroring the GPU arm's N replicas.  Warm-up steps run on a 4 MB
+    prefix (a CPU run has no clocks or JIT to warm; only the allocator and page
+    cache), so that the arm fits the driver's per-N time limit."""
     rank, world, _ = _dist_env()
     if rank != 0:
         return 0
     steps, warm = args.steps, args.warmup
-    # bound the whole run to ~150 s of CPU at ~4 MB/s
-    per_step = 150.0 / max(1, steps + warm)
-    n_ref = int(min(32_000_000, max(1_000_000, per_step * 4.0e6)))
-    text = gen.dna(n_ref)
+    n = args.n
+    reps = max(1, args.gpus)
+    texts = [gen.dna(n, seed=gen.SEED_DNA + r) for r in range(reps)]
     for _ in range(warm):
-        _oracle_time(text)
-    ts = []
-    for _ in range(steps):
-        dt, _sa = _oracle_time(text)
-        ts.append(dt)
+        _oracle_time(texts[0][:4_000_000])
+
+    def one_step():
+        if reps == 1:
+            dt, _sa, _l = _oracle_time(texts[0])
+            return dt
+        t0 = time.perf_counter()
+
+        def work(r):
+            _pin_to_cpu(r)
+            _oracle_time(texts[r])
+        th = [threading.Thread(target=work, args=(r,)) for r in range(reps)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        return time.perf_counter() - t0
+
+    ts = [one_step() for _ in range(steps)]
     total = sum(ts)
-    val = n_ref * steps / 1e6 / total
-    sample = "first %d bytes of the workload per step (oracle port of sais()+lcp_lens(), 1 thread)" % n_ref
+    val = n * reps * steps / 1e6 / total
+    sample = ("all %d bytes of the workload per step and replica (oracle port of sais()+lcp_lens(); the reference is "
+              "single-threaded: %d replica(s) on %d pinned core(s)); warm-up steps on a 4 MB prefix" % (n, reps, reps))
     out = {
         "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": round(total / steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_bytes": N_TEXT, "sample_bytes_per_step": n_ref},
-        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+        "config": _config(n, reps),
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": reps, "kind": "port", "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     _emit(json.dumps(out))
     return 0
+
+
+def _config(n, world):
+    """The `config` object shared verbatim by both arms (same-config check)."""
+    return {"workload": WORKLOAD if n == N_TEXT else "%d-byte G_dna text" % n, "n_bytes_per_gpu": n,
+            "parallelism": "replicas x%d (independent texts, no collective)" % world,
+            "l2": "inputs larger than L2 (text 100 MB + SA 400 MB + LCP 400 MB per step)",
+            "timing": "GPU arm: CUDA events on the launching stream, max over ranks; reference arm: host clock"}
 
 
 def run_gpu(args):
@@ -300,25 +335,25 @@ def run_gpu(args):
                 "kernel_ms_per_launch": round(ind_ms, 4) if ind_ms else None,
                 "share_of_step": round(dom_share, 3) if dom_share else None,
                 "pipeline_bytes_per_input_byte_compulsory": 14, "phases": phases_roof}
-        # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
+        # ---- CPU baseline (oracle port) on the SAME n bytes, rank 0, N=1 only; the SA and LCP the
+        # device-resident loop just built are compared with the oracle's bit for bit
         cpu = None
         if world == 1 and not args.no_cpu:
-            n_cpu = min(n, 32_000_000)
-            dt, sa_cpu = _oracle_time(text[:n_cpu])
-            cpu = {"value": round(n_cpu / 1e6 / dt, 3), "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "first %d bytes of the workload, oracle port of sais()+lcp_lens(), 1 thread of %d host cores"
-                             % (n_cpu, os.cpu_count() or 0), "seconds": round(dt, 2)}
-            # parity spot check on the same sample: GPU SA of the prefix == oracle SA
-            sa_gpu = ctx.build(np.ascontiguousarray(text[:n_cpu]))
-            cpu["gpu_matches_oracle_on_sample"] = bool(np.array_equal(sa_gpu, sa_cpu))
+            dt, sa_cpu, lcp_cpu = _oracle_time(text)
+            cpu = {"value": round(n / 1e6 / dt, 3), "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "all %d bytes of the workload (one step), oracle port of sais()+lcp_lens(), 1 thread of %d host cores"
+                             % (n, os.cpu_count() or 0), "seconds": round(dt, 2)}
+            sa_gpu = d_sa.cpu().numpy().view(np.uint32)
+            lcp_gpu = d_lcp.cpu().numpy().view(np.uint32)
+            cpu["gpu_matches_oracle"] = bool(np.array_equal(sa_gpu, sa_cpu) and np.array_equal(lcp_gpu, lcp_cpu))
+            cpu["gpu_matches_oracle_e2e"] = bool(np.array_equal(h_sa.numpy().view(np.uint32), sa_cpu) and
+                                                 np.array_equal(h_lcp.numpy().view(np.uint32), lcp_cpu))
+            cpu["compared"] = "SA and LCP, all %d entries each, device-resident result and host-API result" % n
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": round(ms_dev / steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if n == N_TEXT else "%d-byte G_dna text" % n, "n_bytes_per_gpu": n,
-                       "parallelism": "replicas x%d (independent texts, no collective)" % world,
-                       "l2": "inputs larger than L2 (text 100 MB + SA 400 MB + LCP 400 MB per step)",
-                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "config": _config(n, world),
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8 * n,
                     "ms_per_step": round(ms_e2e / steps, 3), "api": "b200sa_build_lcp (pinned host buffers)",
                     "result_touch": e2e_result_check},

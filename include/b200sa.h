@@ -36,7 +36,7 @@ typedef struct b200sa_ctx b200sa_ctx;
 
 enum {
     B200SA_OK            =  0,
-    B200SA_ERR_BAD_ARG   = -1,  /* null pointer / bad size                        */
+    B200SA_ERR_BAD_ARG   = -1,  /* null pointer / bad size / (lcp) table not a permutation of 0..n-1 */
     B200SA_ERR_TOO_LARGE = -2,  /* n > B200SA_MAX_N (reference panics above 2^32-1, src/table.rs:380) */
     B200SA_ERR_NO_DEVICE = -3,
     B200SA_ERR_OOM       = -4,
@@ -59,7 +59,9 @@ int b200sa_build(b200sa_ctx *ctx, const uint8_t *text, uint64_t n, uint32_t *sa_
 
 /* Replaces `lcp_lens_quadratic(text, table) -> Vec<u32>` (src/table.rs:348-361)
  * as called by SuffixTable::lcp_lens (src/table.rs:130-138):
- * lcp[0]=0, lcp[i]=|common byte prefix of suffix sa[i-1], suffix sa[i]|. */
+ * lcp[0]=0, lcp[i]=|common byte prefix of suffix sa[i-1], suffix sa[i]|.
+ * `sa` is checked to be a permutation of 0..n-1 (B200SA_ERR_BAD_ARG otherwise; the
+ * reference would panic on an out-of-range index, src/table.rs:356-358). */
 int b200sa_lcp(b200sa_ctx *ctx, const uint8_t *text, uint64_t n,
                const uint32_t *sa, uint32_t *lcp_out);
 

@@ -43,6 +43,8 @@ def lib():
         for name in ("oracle_lcp_quadratic", "oracle_lcp_lens", "oracle_lcp_kasai"):
             getattr(L, name).argtypes = [u8p, u64, u32p, u32p]
             getattr(L, name).restype = ctypes.c_int
+        L.oracle_verify_sa.argtypes = [u8p, u64, u32p]
+        L.oracle_verify_sa.restype = ctypes.c_int64
         L.oracle_positions.argtypes = [u8p, u64, u32p, u8p, u64,
                                        ctypes.POINTER(u64), ctypes.POINTER(u64)]
         L.oracle_positions.restype = ctypes.c_int
@@ -115,6 +117,17 @@ def lcp_lens(text, sa) -> np.ndarray:
 
 def lcp_kasai(text, sa) -> np.ndarray:
     return _lcp(lib().oracle_lcp_kasai, text, sa)
+
+
+def verify_sa(text, sa) -> int:
+    """O(n) check that `sa` is THE suffix array of `text` (permutation + neighbour
+    order through the inverse); 0 = valid, else 1 + index of the first violation."""
+    t = _as_u8(text)
+    sa = np.ascontiguousarray(sa, dtype=np.uint32)
+    assert len(sa) == len(t)
+    rc = int(lib().oracle_verify_sa(_ptr(t), len(t), _ptr(sa)))
+    assert rc >= 0, "oracle_verify_sa: out of memory"
+    return rc
 
 
 def positions(text, sa, query):

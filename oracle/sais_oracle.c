@@ -232,6 +232,38 @@ int oracle_lcp_kasai(const uint8_t *text, uint64_t n, const uint32_t *sa, uint32
     return 0;
 }
 
+/* O(n) suffix-array verifier for sizes where oracle_sais is too slow to be a
+ * per-test oracle (BASELINE config 4, 1 GB).  `sa` is the suffix array of
+ * `text` -- i.e. equals the order of src/table.rs:374 `text[a..].cmp(&text[b..])`,
+ * and by uniqueness the output of the reference's sais() -- iff
+ *   (1) sa is a permutation of 0..n-1, and
+ *   (2) for every i > 0 with a = sa[i-1], b = sa[i]:  T[a] < T[b], or T[a] == T[b]
+ *       and suffix a+1 precedes suffix b+1 (the empty suffix precedes all),
+ *       decided by the inverse permutation.
+ * Returns 0 if valid, 1 + (index of the first violation) otherwise, -1 on OOM. */
+int64_t oracle_verify_sa(const uint8_t *text, uint64_t n, const uint32_t *sa)
+{
+    if (n == 0) return 0;
+    uint32_t *inv = (uint32_t *)malloc((size_t)n * sizeof(uint32_t));
+    if (!inv) return -1;
+    memset(inv, 0xff, (size_t)n * sizeof(uint32_t));
+    for (uint64_t r = 0; r < n; r++) {
+        if (sa[r] >= n || inv[sa[r]] != 0xffffffffu) { free(inv); return 1 + (int64_t)r; }
+        inv[sa[r]] = (uint32_t)r;
+    }
+    for (uint64_t i = 1; i < n; i++) {
+        uint64_t a = sa[i - 1], b = sa[i];
+        int ok;
+        if (text[a] != text[b]) ok = text[a] < text[b];
+        else if (a + 1 == n) ok = 1;             /* "c" precedes "c..." */
+        else if (b + 1 == n) ok = 0;
+        else ok = inv[a + 1] < inv[b + 1];
+        if (!ok) { free(inv); return 1 + (int64_t)i; }
+    }
+    free(inv);
+    return 0;
+}
+
 /* ---- queries: src/table.rs:197-293, 900-914 ---- */
 
 /* table.rs:900-914 binary_search: first index whose predicate is true */

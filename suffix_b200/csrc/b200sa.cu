@@ -612,6 +612,25 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
     uint32_t n32 = (uint32_t)n;
     TRY(ensure(c, c->isa, (size_t)n * 4));
     if (!reuse_pack) {
+        // stand-alone call: the table comes from the caller (from_parts accepts anything,
+        // src/table.rs:111-119, and the reference would merely panic on a bad index), and
+        // every LCP kernel indexes text and phi with sa[r]: check that it is a permutation
+        // of 0..n-1 before trusting it
+        TRY(mark(c, "lcp_validate"));
+        TRY(ensure(c, c->small, 4096));
+        uint64_t nwv = (n + 31) / 32;
+        uint32_t *seen = ptr<uint32_t>(c->isa);             // free until the Phi path needs it
+        uint32_t *bad = ptr<uint32_t>(c->small) + 12;
+        CU_TRY(c, cudaMemsetAsync(seen, 0, nwv * 4, c->stream));
+        CU_TRY(c, cudaMemsetAsync(bad, 0, 4, c->stream));
+        LAUNCH(c, k_sa_validate, cdiv(n, BLK), d_sa, n32, seen, bad);
+        TRY(read_words(c, bad, 1));
+        if (c->h_pin[0] != 0) {
+            c->last_error = "table is not a permutation of 0..n-1 (index out of range or repeated)";
+            return B200SA_ERR_BAD_ARG;
+        }
+    }
+    if (!reuse_pack) {
         // stand-alone call: byte histogram -> alphabet -> packed text
         TRY(mark(c, "lcp_pack"));
         const uint8_t *text = d_text;
@@ -722,7 +741,7 @@ const char *b200sa_strerror(int code) {
     switch (code) {
         case B200SA_OK: return "ok";
         case B200SA_ERR_BAD_ARG: return "bad argument";
-        case B200SA_ERR_TOO_LARGE: return "text longer than 2^32-1 bytes";
+        case B200SA_ERR_TOO_LARGE: return "text longer than B200SA_MAX_N = 2^32-4096 bytes";
         case B200SA_ERR_NO_DEVICE: return "no usable CUDA device";
         case B200SA_ERR_OOM: return "out of device memory";
         case B200SA_ERR_CUDA: return "CUDA error";
@@ -857,8 +876,8 @@ int b200sa_build_lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint3
     return rc;
 }
 
-static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *sa_out, uint32_t *lcp_out,
-                      const uint32_t *sa_in) {
+static int host_build_inner(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *sa_out, uint32_t *lcp_out,
+                            const uint32_t *sa_in) {
     if (n > B200SA_MAX_N) { c->last_error = "text longer than 2^32-4096 bytes"; return B200SA_ERR_TOO_LARGE; }
     CU_TRY(c, cudaSetDevice(c->device));
     begin_call(c, nullptr);
@@ -883,7 +902,7 @@ static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *
         c->early_done = false;
         int brc = build_dev(c, ptr<uint8_t>(c->text), n, ptr<uint32_t>(c->sa));
         c->early_sa_out = nullptr;
-        if (brc != B200SA_OK) { cudaStreamSynchronize(c->copy_stream); return brc; }
+        if (brc != B200SA_OK) return brc;
         if (sa_out && c->early_done) {
             TRY(mark(c, "d2h_sa"));      // already on its way on the copy stream
         } else if (sa_out) {
@@ -907,6 +926,21 @@ static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->copy_stream));
     return end_call(c);
+}
+
+// Every exit of the host API passes through here: on failure, D2H copies into the caller's
+// buffers may still be in flight on either stream, and the caller is free to release the
+// buffers as soon as we return.
+static int host_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *sa_out, uint32_t *lcp_out,
+                      const uint32_t *sa_in) {
+    int rc = host_build_inner(c, text, n, sa_out, lcp_out, sa_in);
+    if (rc != B200SA_OK) {
+        c->early_sa_out = nullptr;
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 int b200sa_build(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *sa_out) {

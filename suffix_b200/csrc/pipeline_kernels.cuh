@@ -333,6 +333,21 @@ __global__ void __launch_bounds__(BLK) k_lcp_direct(const void *__restrict__ pte
     if (h == cap && room > cap) atomicAdd(capped, 1u);
 }
 
+// lcp-only entry points: the caller's table must be a permutation of 0..n-1 (every LCP
+// kernel indexes text / phi with sa[r]).  *bad counts out-of-range and repeated entries.
+__global__ void __launch_bounds__(BLK) k_sa_validate(const uint32_t *__restrict__ sa, uint32_t n, uint32_t *seen,
+                                                     uint32_t *bad) {
+    uint32_t r = blockIdx.x * BLK + threadIdx.x;
+    if (r >= n) return;
+    uint32_t s = sa[r];
+    bool wrong = s >= n;
+    if (!wrong) {
+        uint32_t bit = 1u << (s & 31);
+        wrong = (atomicOr(&seen[s >> 5], bit) & bit) != 0;
+    }
+    if (wrong) atomicAdd(bad, 1u);
+}
+
 constexpr uint32_t PHI_NONE = 0xffffffffu;
 __global__ void __launch_bounds__(BLK) k_phi(const uint32_t *__restrict__ sa, uint32_t n, uint32_t *phi) {
     uint32_t r = blockIdx.x * BLK + threadIdx.x;

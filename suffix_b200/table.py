@@ -27,14 +27,14 @@ class SuffixTable:
 
     def __init__(self, text, *, device: int = 0, _table=None):
         """SuffixTable::new (src/table.rs:78-85): O(n) construction on the GPU.
-        Raises if the text exceeds 2^32-1 bytes (the reference panics, :380)."""
+        Raises if the text exceeds B200SA_MAX_N = 2^32-4096 bytes (the reference panics above 2^32-1, :380)."""
         self._text = _as_bytes(text)
         self._device = device
         if _table is not None:
             self._table = _table
             return
         if len(self._text) > 0xFFFFF000:   # B200SA_MAX_N
-            raise OverflowError("text longer than 2^32-1 bytes")
+            raise OverflowError("text longer than 2^32-4096 bytes (B200SA_MAX_N)")
         t = np.frombuffer(self._text, dtype=np.uint8)
         with _lock:                           # default context is not thread-safe
             ctx = _lib.default_context(device)
@@ -95,13 +95,18 @@ class SuffixTable:
         empty = tab[0:0]
         if n == 0 or len(q) == 0:
             return empty
-        s0 = text[int(tab[0]):]
-        if (q < s0 and not s0.startswith(q)) or q > text[int(tab[n - 1]):]:
+        m = len(q)
+        # bounded heads instead of whole suffixes: `q <= text[s..]` <=> `q <= text[s..s+m]`
+        # (O(m) per probe, no copy of the suffix -- like the reference's slice compares)
+        h0 = text[int(tab[0]):int(tab[0]) + m]
+        hl = text[int(tab[n - 1]):int(tab[n - 1]) + m]
+        if q < h0 or q > hl:                  # :228-235 (q < s0 && !s0.starts_with(q)) || q > last
             return empty
         lo, hi = 0, n                         # binary_search, :900-914
         while lo < hi:
             mid = (lo + hi) // 2
-            if q <= text[int(tab[mid]):]:
+            s = int(tab[mid])
+            if q <= text[s:s + m]:
                 hi = mid
             else:
                 lo = mid + 1

@@ -10,3 +10,4 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "slow: full-size configs (minutes); deselect with -m 'gpu and not slow' while iterating")

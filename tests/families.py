@@ -15,6 +15,12 @@ def kat():
         return json.load(f)
 
 
+def full_size():
+    """SHA-256 goldens of BASELINE configs 2 and 3 at full size (make_full_size.py)."""
+    with open(os.path.join(GOLDEN, "full_size.json")) as f:
+        return json.load(f)
+
+
 def fib_word(n):
     a, b = b"a", b"ab"
     while len(b) < n:

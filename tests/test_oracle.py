@@ -104,3 +104,41 @@ def test_generators_shapes():
     e = gen.english(5000)
     e.tobytes().decode("utf-8")
     assert len(e) == 5000
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.binary(min_size=2, max_size=200), st.data())
+def test_verify_sa(t, data):
+    """oracle.verify_sa accepts exactly the suffix array (used for BASELINE config 4,
+    where sais() itself is too slow to be a per-test oracle)."""
+    sa = oracle.naive_sa(t)
+    assert oracle.verify_sa(t, sa) == 0
+    i = data.draw(st.integers(0, len(t) - 2))
+    bad = sa.copy()
+    bad[[i, i + 1]] = bad[[i + 1, i]]          # any transposition breaks the (unique) order
+    assert oracle.verify_sa(t, bad) != 0
+    dup = sa.copy()
+    dup[i] = dup[i + 1]
+    assert oracle.verify_sa(t, dup) != 0
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.binary(max_size=120), st.binary(min_size=1, max_size=4))
+def test_host_mirror_positions(t, q):
+    """The Python mirror's positions()/any_position() (host binary search over text +
+    table, src/table.rs:223-293) against the oracle's restatement, on tables built by
+    the oracle (from_parts: no GPU involved)."""
+    from suffix_b200.table import SuffixTable
+    sa = oracle.naive_sa(t)
+    tab = SuffixTable.from_parts(t, sa)
+    s, e = oracle.positions(t, sa, q)
+    assert tab.positions(q).tolist() == sa[s:e].tolist()
+    want = [i for i in range(len(t)) if t.startswith(q, i)]
+    assert sorted(tab.positions(q).tolist()) == want
+    hit = tab.any_position(q)
+    assert (hit in want) if want else hit is None
+
+
+def test_full_size_goldens_present():
+    fs = families.full_size()
+    assert set(fs) == {"G_dna_100MB", "G_bytes_100MB"} and all(len(v["sa_sha256"]) == 64 for v in fs.values())
