@@ -122,12 +122,17 @@ int b200sa_shard_classify(b200sa_ctx *ctx, const uint8_t *d_shard, uint64_t len,
 typedef struct {
     uint64_t n;               /* text bytes of the last build                     */
     uint64_t m;               /* LMS suffixes at level 0                          */
-    uint64_t names;           /* distinct LMS substrings (reduced alphabet)       */
-    uint32_t doubling_rounds; /* rank-pair doubling rounds on the reduced string  */
+    uint64_t names;           /* robust path: distinct LMS substrings (reduced alphabet);
+                                 direct path: LMS suffixes settled by the first window */
+    uint32_t doubling_rounds; /* robust path: rank-pair doubling rounds on the reduced
+                                 string; direct path: window rounds of the LMS sort */
     uint32_t kernel_launches; /* kernels launched by the last call                */
     uint32_t induce_blocks;   /* grid of the persistent induce kernels            */
     uint32_t sm_count;
     uint64_t workspace_bytes; /* device workspace currently held                  */
+    uint32_t direct_sort;     /* 1: LMS suffixes sorted directly by character windows;
+                                 0: robust path (stage-1 induce + naming + doubling) */
+    uint32_t reserved;
 } b200sa_stats;
 
 int b200sa_last_stats(b200sa_ctx *ctx, b200sa_stats *out);

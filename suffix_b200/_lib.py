@@ -19,7 +19,7 @@ class Stats(ctypes.Structure):
     _fields_ = [("n", ctypes.c_uint64), ("m", ctypes.c_uint64), ("names", ctypes.c_uint64),
                 ("doubling_rounds", ctypes.c_uint32), ("kernel_launches", ctypes.c_uint32),
                 ("induce_blocks", ctypes.c_uint32), ("sm_count", ctypes.c_uint32),
-                ("workspace_bytes", ctypes.c_uint64)]
+                ("workspace_bytes", ctypes.c_uint64), ("direct_sort", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 _lib = None

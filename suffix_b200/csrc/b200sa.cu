@@ -20,6 +20,7 @@
 #include "classify.cuh"
 #include "induce.cuh"
 #include "pipeline_kernels.cuh"
+#include "lms_sort.cuh"
 
 using namespace b200sa;
 
@@ -61,7 +62,8 @@ struct b200sa_ctx {
     DevBuf blkstate, carry, tables, small, scan_partial, radix_cnt, blkcnt;
     DevBuf os_hist, os_status, phik, phiv, runscr, plcp_samp;
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
-    DevBuf packed;
+    DevBuf packed, scan_state;
+    uint32_t scan_epoch = 0, scan_tiles_cap = 0;
     uint32_t sigma = 256;            // distinct bytes of the current text
     int bits = 8;                    // bits per char of the packed text of the current call (2, 4 or 8 = raw)
     const void *ptext = nullptr;     // packed words, or the byte text when bits == 8
@@ -158,6 +160,9 @@ static int read_words(b200sa_ctx *c, const uint32_t *dsrc, int count) {
 }
 
 // ------------------------------------------------------- generic primitives
+// Single-pass scan (k_scan_lb, common.cuh): one launch, the input functor is evaluated once
+// per element.  The tile descriptors live in c->scan_state and are epoch-tagged, so nothing
+// is cleared between scans; a (re)allocated buffer is zeroed once (epochs start at 2).
 template <class Op, class InF, class OutF>
 static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, typename Op::T *d_total) {
     typedef typename Op::T T;
@@ -166,11 +171,21 @@ static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, typename Op::T 
         return B200SA_OK;
     }
     uint32_t nb = cdiv(n, SCAN_CHUNK);
-    TRY(ensure(c, c->scan_partial, (size_t)nb * sizeof(T)));
-    T *part = ptr<T>(c->scan_partial);
-    LAUNCH(c, (k_scan_reduce<Op, InF>), nb, in, n, part);
-    LAUNCH(c, (k_scan_partials<Op>), 1, part, nb, d_total);
-    LAUNCH(c, (k_scan_apply<Op, InF, OutF>), nb, in, out, n, part);
+    size_t need = (size_t)nb * 20 + 64;
+    if (c->scan_state.cap < need) {
+        TRY(ensure(c, c->scan_state, need * 2));
+        CU_TRY(c, cudaMemsetAsync(c->scan_state.p, 0, c->scan_state.cap, c->stream));
+        c->scan_tiles_cap = (uint32_t)((c->scan_state.cap - 64) / 20);
+    }
+    ScanState S;
+    uint8_t *basep = ptr<uint8_t>(c->scan_state);
+    S.ticket = reinterpret_cast<uint32_t *>(basep);
+    S.agg = reinterpret_cast<unsigned long long *>(basep + 64);
+    S.incl = S.agg + c->scan_tiles_cap;
+    S.flag = reinterpret_cast<uint32_t *>(S.incl + c->scan_tiles_cap);
+    c->scan_epoch += 2;
+    S.epoch = c->scan_epoch;
+    LAUNCH(c, (k_scan_lb<Op, InF, OutF>), nb, in, out, n, nb, S, d_total);
     CU_TRY(c, cudaGetLastError());
     return B200SA_OK;
 }
@@ -224,6 +239,49 @@ static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, u
         LAUNCH(c, (k_os_pass<K, LoadArr<K>, LoadArr<uint32_t>>), tiles, LoadArr<K>{ka}, LoadArr<uint32_t>{va}, kb, vb, n,
                (uint32_t)(8 * p), ghist + p * 256,
                reinterpret_cast<volatile unsigned long long *>(c->os_status.p), ticket + p);
+        K *tk = ka; ka = kb; kb = tk;
+        uint32_t *tv = va; va = vb; vb = tv;
+    }
+    CU_TRY(c, cudaGetLastError());
+    *kout = ka;
+    *vout = va;
+    return B200SA_OK;
+}
+
+// Same sort, but the first pass reads its (key, value) items from functors (no materialised
+// input arrays); at least one pass runs, so the result always lands in a buffer pair.
+template <class K, class KeyF, class ValF>
+static int sort_pairs_from(b200sa_ctx *c, KeyF keyf, ValF valf, K *ka, uint32_t *va, K *kb, uint32_t *vb, uint64_t n,
+                           int bits, K **kout, uint32_t **vout) {
+    *kout = ka;
+    *vout = va;
+    if (n == 0) return B200SA_OK;
+    int npass = (bits + 7) / 8;
+    if (npass < 1) npass = 1;
+    if (npass > OS_MAX_PASSES) npass = OS_MAX_PASSES;
+    uint32_t tiles = cdiv(n, TILE);
+    size_t status_bytes = (size_t)tiles * 256 * 8;
+    TRY(ensure(c, c->os_hist, OS_MAX_PASSES * 256 * 4 + 64));
+    TRY(ensure(c, c->os_status, status_bytes));
+    uint32_t *ghist = ptr<uint32_t>(c->os_hist);
+    uint32_t *ticket = ghist + OS_MAX_PASSES * 256;
+    CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
+    uint32_t hb = tiles < 1184u ? tiles : 1184u;
+    {
+        size_t shm = (size_t)NWARP * npass * 256 * 4;
+        auto kfn = k_os_hist<K, KeyF>;
+        CU_TRY(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NWARP * OS_MAX_PASSES * 256 * 4)));
+        kfn<<<hb, BLK, shm, c->stream>>>(keyf, n, npass, 0u, ghist);
+        c->launches++;
+    }
+    LAUNCH(c, k_os_scan, (uint32_t)npass, ghist);
+    volatile unsigned long long *status = reinterpret_cast<volatile unsigned long long *>(c->os_status.p);
+    CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
+    LAUNCH(c, (k_os_pass<K, KeyF, ValF>), tiles, keyf, valf, ka, va, n, 0u, ghist, status, ticket);
+    for (int p = 1; p < npass; p++) {
+        CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
+        LAUNCH(c, (k_os_pass<K, LoadArr<K>, LoadArr<uint32_t>>), tiles, LoadArr<K>{ka}, LoadArr<uint32_t>{va}, kb, vb, n,
+               (uint32_t)(8 * p), ghist + p * 256, status, ticket + p);
         K *tk = ka; ka = kb; kb = tk;
         uint32_t *tv = va; va = vb; vb = tv;
     }
@@ -393,6 +451,118 @@ static int pack_text(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t si
     return B200SA_OK;
 }
 
+// ------------------------------------------------------- direct LMS-suffix sort
+// lms_sort.cuh: radix sort of the LMS suffixes by character windows + refinement of the
+// tied groups.  On success *list_out points at the LMS suffixes in suffix order (the
+// seed of the final induce).  *done = false: the text has long repeats (groups stay tied);
+// the caller takes the robust path (stage-1 induce, naming, rank doubling).
+static uint32_t window_chars(uint32_t sigma, int bits, uint64_t *range_out) {
+    if (bits == 2) { *range_out = 1ull << 32; return 16; }
+    if (sigma < 2) sigma = 2;
+    uint32_t cap = bits == 4 ? 13u : 8u, k = 0;
+    uint64_t r = 1;
+    while (k < cap && r * sigma <= (1ull << 32)) { r *= sigma; k++; }
+    *range_out = r;
+    return k;
+}
+
+template <int BITS>
+static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **list_out, bool *done) {
+    *done = false;
+    uint64_t range = 0;
+    LmsWin W;
+    W.ptext = c->ptext; W.code_of = ptr<uint32_t>(c->tables) + T_CODE; W.n = n;
+    W.sigma = BITS == 2 ? 4u : c->sigma;
+    W.kc = window_chars(c->sigma, BITS, &range);
+    const uint32_t kc = W.kc;
+    TRY(ensure(c, c->k32b, (size_t)m * 4));
+    TRY(ensure(c, c->reduced, (size_t)m * 4));
+    TRY(ensure(c, c->v0, (size_t)m * 4));
+    TRY(ensure(c, c->v1, (size_t)m * 4));
+    TRY(ensure(c, c->small, 4096));
+    uint32_t *sm = ptr<uint32_t>(c->small);
+    uint32_t *Ks, *Ps;
+    TRY(mark(c, "lms_sort"));
+    TRY((sort_pairs_from<uint32_t>(c, LmsKeyDesc<BITS>{W, ptr<uint32_t>(c->lmspos), m},
+                                   LmsValDesc{ptr<uint32_t>(c->lmspos), m}, ptr<uint32_t>(c->k32b), ptr<uint32_t>(c->v0),
+                                   ptr<uint32_t>(c->reduced), ptr<uint32_t>(c->v1), m, bit_length(range - 1), &Ks, &Ps)));
+    // groups of equal windows; members of non-singleton groups -> active list
+    TRY(mark(c, "lms_groups"));
+    TRY(ensure(c, c->p0, (size_t)m * 4));
+    TRY(ensure(c, c->p1, (size_t)m * 4));
+    TRY(ensure(c, c->g0, (size_t)m * 4));
+    TRY(ensure(c, c->g1, (size_t)m * 4));
+    TRY(ensure(c, c->sa_r, (size_t)m * 4));
+    TRY(ensure(c, c->rank, (size_t)m * 4));
+    uint32_t *slotA = ptr<uint32_t>(c->p0), *slotB = ptr<uint32_t>(c->p1);
+    uint32_t *grpA = ptr<uint32_t>(c->g0), *grpB = ptr<uint32_t>(c->g1);
+    uint32_t *posA = ptr<uint32_t>(c->sa_r), *posB = ptr<uint32_t>(c->rank);
+    unsigned long long *d_tot = reinterpret_cast<unsigned long long *>(sm + 16);
+    TRY((dev_scan<OpMaxSum>(c, InLmsGroup1{Ks, Ps, m, n, kc}, OutLmsCompact1{Ps, slotA, posA, grpA}, m, d_tot)));
+    TRY(read_words(c, sm + 16, 1));
+    uint32_t na = c->h_pin[0];
+    c->stats.names = m - na;                       // LMS suffixes settled by the first window
+    uint32_t rounds = 1;
+    uint32_t max_rounds = 6;
+    if (const char *e = getenv("B200SA_DIRECT_ROUNDS")) { int v = atoi(e); if (v >= 1) max_rounds = (uint32_t)v; }
+    if (getenv("B200SA_TRACE")) fprintf(stderr, "[b200sa] direct LMS sort: kc=%u, round 1 leaves %u of %u tied\n", kc, na, m);
+    if ((uint64_t)na * 10 > (uint64_t)m * 9 && m > 64) return B200SA_OK;   // the window tells nothing apart: long repeats
+    uint64_t h = kc;
+    bool try_local = getenv("B200SA_NO_LOCAL_SORT") == nullptr;
+    const int gbits = 32 + bit_length(m);
+    while (na > 0) {
+        if (rounds >= max_rounds) return B200SA_OK;            // still tied: robust path
+        rounds++;
+        {
+            static const char *kNames[] = {"lms_refine2", "lms_refine3", "lms_refine4", "lms_refine5", "lms_refineN"};
+            TRY(mark(c, kNames[rounds - 2 < 4 ? rounds - 2 : 4]));
+        }
+        TRY(ensure(c, c->k64a, (size_t)na * 8));
+        TRY(ensure(c, c->k64b, (size_t)na * 8));
+        TRY(ensure(c, c->sorted, (size_t)m * 4));
+        uint64_t *KA = ptr<uint64_t>(c->k64a), *KB = ptr<uint64_t>(c->k64b), *K2 = nullptr;
+        uint32_t *scratch = ptr<uint32_t>(c->sorted), *P2 = nullptr;
+        LAUNCH(c, (k_lms_refine_keys<BITS>), cdiv(na, BLK), W, posA, grpA, na, (uint32_t)h, KA);
+        const uint32_t span = (uint32_t)(h + kc > 0xffffffffull ? 0xffffffffull : h + kc);
+        bool local_ok = false;
+        if (try_local) {                         // tiny groups: rank inside the group by counting
+            CU_TRY(c, cudaMemsetAsync(sm + 24, 0, 4, c->stream));
+            LAUNCH(c, k_group_local_sort, cdiv(na, BLK), KA, posA, na, 32u, KB, scratch, sm + 24);
+            TRY((dev_scan<OpMaxSum>(c, InLmsGroupR{KB, scratch, slotA, na, n, span},
+                                    OutLmsCompactR{scratch, slotA, Ps, slotB, posB, grpB}, na, d_tot)));
+            TRY(read_words(c, sm + 16, 9));          // [0] tied count ... [8] = sm[24] overflow flag
+            local_ok = c->h_pin[8] == 0;
+            if (!local_ok) try_local = false;        // some group is large: radix sort from now on
+        }
+        if (!local_ok) {
+            TRY(sort_pairs<uint64_t>(c, KA, posA, KB, scratch, na, gbits, &K2, &P2));
+            // (posA may now hold sorted values; the compaction below writes posB)
+            TRY((dev_scan<OpMaxSum>(c, InLmsGroupR{K2, P2, slotA, na, n, span},
+                                    OutLmsCompactR{P2, slotA, Ps, slotB, posB, grpB}, na, d_tot)));
+            TRY(read_words(c, sm + 16, 1));
+        }
+        uint32_t na_next = c->h_pin[0];
+        if (getenv("B200SA_TRACE")) fprintf(stderr, "[b200sa] direct LMS sort: round %u (h=%llu): %u -> %u tied\n", rounds, (unsigned long long)h, na, na_next);
+        // slow convergence on a large residue means long repeats: stop early
+        if (rounds >= 3 && (uint64_t)na_next * 2 > na && (uint64_t)na_next * 64 > m) return B200SA_OK;
+        na = na_next;
+        uint32_t *t;
+        t = slotA; slotA = slotB; slotB = t;
+        t = posA; posA = posB; posB = t;
+        t = grpA; grpA = grpB; grpB = t;
+        h += kc;
+    }
+    c->stats.doubling_rounds = rounds;
+    *list_out = Ps;
+    *done = true;
+    return B200SA_OK;
+}
+static int lms_direct_sort(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **list_out, bool *done) {
+    if (c->bits == 2) return lms_direct_sort_t<2>(c, n, m, list_out, done);
+    if (c->bits == 4) return lms_direct_sort_t<4>(c, n, m, list_out, done);
+    return lms_direct_sort_t<8>(c, n, m, list_out, done);
+}
+
 // ------------------------------------------------------- induce launcher
 static const void *induce_fn(bool spass, int bits) {
     if (bits == 2) return spass ? (const void *)k_induce<true, 2> : (const void *)k_induce<false, 2>;
@@ -512,7 +682,15 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     TRY(ensure(c, c->blkcnt, (size_t)2 * c->induce_blocks * 256 * 4));
     TRY(ensure(c, c->runscr, (size_t)2 * TILE * 4));
     uint32_t *lmslist = ptr<uint32_t>(c->lmslist);
-    if (m > 0) {
+    bool direct_done = false;
+    if (m > 0 && !getenv("B200SA_NO_DIRECT")) {
+        uint32_t *lst = nullptr;
+        TRY(lms_direct_sort(c, n32, m, &lst, &direct_done));
+        if (direct_done) lmslist = lst;
+    }
+    c->stats.direct_sort = direct_done ? 1u : 0u;
+    if (m > 0 && !direct_done) {
+        c->stats.doubling_rounds = 0;
         TRY(ensure(c, c->sorted, (size_t)m * 4));
         TRY(ensure(c, c->flag, m));
         TRY(ensure(c, c->reduced, (size_t)m * 4));
@@ -805,7 +983,7 @@ void b200sa_ctx_destroy(b200sa_ctx *c) {
     DevBuf *bufs[] = {&c->text, &c->sa, &c->lcp, &c->pred, &c->stype, &c->lmsb, &c->lmsrank, &c->lmspos, &c->lmslist,
                       &c->lmspred, &c->sorted, &c->flag, &c->reduced, &c->sa_r, &c->blkstate, &c->carry, &c->tables,
                       &c->small, &c->scan_partial, &c->radix_cnt, &c->blkcnt, &c->k32b, &c->k64a, &c->k64b, &c->v0,
-                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr, &c->plcp_samp};
+                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr, &c->plcp_samp, &c->scan_state};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);

@@ -181,6 +181,127 @@ __global__ void __launch_bounds__(BLK) k_scan_apply(InF in, OutF out, uint64_t n
     }
 }
 
+// ---------------------------------------------------- single-pass device scan
+// Decoupled look-back (one kernel, the input is read ONCE): tiles are claimed in
+// order through an atomic ticket; a tile publishes its aggregate, warp 0 walks
+// back over the predecessors' descriptors (32 at a time) until it meets an
+// inclusive prefix, publishes its own inclusive prefix and the block applies it.
+// Descriptor per tile: agg (u64), incl (u64), flag (u32).  Flags are epoch-tagged
+// (epoch+1 = aggregate ready, epoch+2 = inclusive ready; the host bumps the epoch
+// by 2 per scan), so the descriptor arrays never need clearing between scans; the
+// ticket is reset by the block that draws the last tile.  Value before flag with a
+// gpu-scope fence in between on the writer side, flag before value on the reader
+// side.  All ops used here are commutative and associative.
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+template <class T>
+__device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(FULL, v, src); }
+
+struct ScanState {
+    unsigned long long *agg;     // [tiles]
+    unsigned long long *incl;    // [tiles]
+    uint32_t *flag;              // [tiles]
+    uint32_t *ticket;            // [1], zero between kernels
+    uint32_t epoch;
+};
+
+template <class Op, class InF, class OutF>
+__global__ void __launch_bounds__(BLK) k_scan_lb(InF in, OutF out, uint64_t n, uint32_t ntiles, ScanState S,
+                                                 typename Op::T *d_total) {
+    typedef typename Op::T T;
+    __shared__ T s_w[NWARP + 1];
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) {
+        uint32_t t = atomicAdd(S.ticket, 1u);
+        if (t + 1 == ntiles) *S.ticket = 0u;         // every tile has been drawn: re-arm for the next kernel
+        s_tile = t;
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile, w = warp_id(), l = lane_id();
+    const uint64_t base = (uint64_t)tile * SCAN_CHUNK + (uint64_t)w * (SCAN_IPT * 32) + l;
+    T v[SCAN_IPT], exc[SCAN_IPT];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        uint64_t i = base + (uint64_t)k * 32;
+        v[k] = (i < n) ? (T)in(i) : Op::id();
+    }
+    T carry = Op::id();
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        T inc = warp_incl_scan<Op>(v[k]);
+        T prev = __shfl_up_sync(FULL, inc, 1);
+        exc[k] = Op::op(carry, l == 0 ? Op::id() : prev);
+        carry = Op::op(carry, shfl_t(inc, 31));
+    }
+    if (l == 0) s_w[w] = carry;           // warp totals
+    __syncthreads();
+    if (w == 0) {
+        T t = (l < (uint32_t)NWARP) ? s_w[l] : Op::id();
+        T inc = warp_incl_scan<Op>(t);
+        const T block_total = shfl_t(inc, NWARP - 1);
+        T prevw = __shfl_up_sync(FULL, inc, 1);
+        T wexc = (l == 0) ? Op::id() : prevw;          // exclusive prefix of warp l inside the block
+        T prefix = Op::id();
+        if (tile > 0) {
+            if (l == 0) {
+                st_relaxed_u64(S.agg + tile, (unsigned long long)block_total);
+                __threadfence();
+                st_relaxed_u32(S.flag + tile, S.epoch + 1u);
+            }
+            int64_t t0 = (int64_t)tile - 1;
+            while (true) {
+                int64_t tt = t0 - (int64_t)l;            // lane 0: nearest predecessor
+                uint32_t st = 2u;                         // before tile 0: inclusive prefix = identity
+                T val = Op::id();
+                if (tt >= 0) {
+                    uint32_t f;
+                    do { f = ld_relaxed_u32(S.flag + tt) - S.epoch; } while (f != 1u && f != 2u);
+                    __threadfence();
+                    st = f;
+                    val = (T)ld_relaxed_u64((f == 2u ? S.incl : S.agg) + tt);
+                }
+                uint32_t im = __ballot_sync(FULL, st == 2u);
+                uint32_t first = im ? (uint32_t)(__ffs(im) - 1) : 32u;
+                T contrib = (l <= first) ? val : Op::id();
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib = Op::op(contrib, __shfl_xor_sync(FULL, contrib, o));
+                prefix = Op::op(prefix, contrib);
+                if (im) break;
+                t0 -= 32;
+            }
+        }
+        if (l == 0) {
+            T total = Op::op(prefix, block_total);
+            st_relaxed_u64(S.incl + tile, (unsigned long long)total);
+            __threadfence();
+            st_relaxed_u32(S.flag + tile, S.epoch + 2u);
+            if (tile + 1 == ntiles && d_total) *d_total = total;
+        }
+        if (l < (uint32_t)NWARP) s_w[l] = Op::op(prefix, wexc);
+    }
+    __syncthreads();
+    const T wbase = s_w[w];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        uint64_t i = base + (uint64_t)k * 32;
+        if (i < n) out(i, Op::op(wbase, exc[k]), v[k]);
+    }
+}
+
 // ------------------------------------------------------------- tile ranking
 // Stable multi-way ranking of one tile (TILE items, warp-blocked layout:
 // warp w, round r, lane l owns logical item  w*ITEMS*32 + r*32 + l).

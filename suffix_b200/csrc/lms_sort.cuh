@@ -1,0 +1,151 @@
+// lms_sort.cuh -- direct sort of the LMS suffixes ("LMS substring bucket sort" +
+// "rank/rename" of the north-star pipeline, fused into one radix sort with
+// refinement): replaces, for texts whose LMS suffixes are told apart by a few
+// windows of characters, the reference's stage-1 machinery
+//   P5  LMS into bucket tails            src/table.rs:411-416
+//   P7/P9 first L/S induce               src/table.rs:421-448
+//   P10 compaction, P11 naming, P12      src/table.rs:450-492 (wstring_equal :802-820)
+//   P13 recursion on the reduced string  src/table.rs:494-506
+//   P15/P16 un-rename                    src/table.rs:512-530
+// whose only product is "the LMS suffixes in suffix order" (the seed of the final
+// induce, P18, src/table.rs:536-541).
+//
+// Formulation.  A window key packs the next KC characters of a suffix, first
+// character most significant, as a base-sigma number of dense order-preserving
+// codes (sigma^KC <= 2^32; for 2-bit packed text simply the 16 two-bit codes), with
+// zeros past the end of the text.
+//   round 1: one-sweep LSD radix sort of (window(p), p) over all LMS positions;
+//   round r: the members of groups that are still tied after (r-1)*KC characters are
+//            ordered inside their group by the next window (MSD refinement; tiny
+//            groups by counting, otherwise radix on (group, window)).
+// End of text (src/table.rs:374: a proper prefix sorts first, there is no sentinel):
+// the first sort is fed in DESCENDING text position and every later sort is stable,
+// so inside a group of equal padded keys the order is always descending position.
+// A member whose window runs past n ("truncated", p + h + KC > n) is a proper prefix
+// of every non-truncated member with the same padded key and of every truncated
+// member before which it stands, so truncated members are final exactly where the
+// stable sort leaves them and each forms a group of its own.
+// Texts that stay tied (long repeats: LCP >> KC * rounds) are handed to the robust
+// path (stage-1 induce + naming + rank doubling); see lms_direct_sort() in b200sa.cu.
+#pragma once
+#include "classify.cuh"
+
+namespace b200sa {
+
+struct LmsWin {
+    const void *ptext;            // packed words (BITS 2/4) or the byte text (BITS 8)
+    const uint32_t *code_of;      // [256] dense codes (BITS 8, sigma < 256)
+    uint32_t n, sigma, kc;        // kc = characters per window
+};
+
+// pair-reversal of 16 two-bit groups: char 0 (low bits) becomes the most significant
+__device__ __forceinline__ uint32_t rev_pairs(uint32_t x) {
+    uint32_t y = __brev(x);
+    return ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);
+}
+
+// window key of text[p .. p+kc), zero-padded past n;  p <= n
+template <int BITS>
+__device__ __forceinline__ uint32_t lms_window(const LmsWin &W, uint32_t p) {
+    const uint32_t left = W.n - p;                 // valid characters from p on
+    if (BITS == 2) {
+        if (left == 0) return 0u;
+        uint32_t x = text_bits<2>(W.ptext, p);
+        if (left < 16u) x &= (1u << (2u * left)) - 1u;
+        return rev_pairs(x);
+    } else if (BITS == 4) {
+        if (left == 0) return 0u;
+        uint32_t lo = text_bits<4>(W.ptext, p);
+        uint32_t hi = (W.kc > 8u && left > 8u) ? text_bits<4>(W.ptext, p + 8u) : 0u;
+        uint32_t key = 0;
+        for (uint32_t i = 0; i < W.kc; i++) {
+            uint32_t c = (i < 8u ? (lo >> (4u * i)) : (hi >> (4u * (i - 8u)))) & 15u;
+            key = key * W.sigma + (i < left ? c : 0u);
+        }
+        return key;
+    } else {
+        const uint8_t *t = reinterpret_cast<const uint8_t *>(W.ptext);
+        uint32_t key = 0;
+        if (W.sigma == 256u) {
+#pragma unroll
+            for (uint32_t i = 0; i < 4u; i++) key = (key << 8) | (i < left ? (uint32_t)__ldg(t + p + i) : 0u);
+            return key;
+        }
+        for (uint32_t i = 0; i < W.kc; i++) {
+            uint32_t c = i < left ? __ldg(W.code_of + __ldg(t + p + i)) : 0u;
+            key = key * W.sigma + c;
+        }
+        return key;
+    }
+}
+
+// first-pass functors of the one-sweep sort: item i = LMS position lmspos[m-1-i]
+template <int BITS>
+struct LmsKeyDesc {
+    LmsWin W; const uint32_t *lmspos; uint32_t m;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const {
+        return lms_window<BITS>(W, __ldg(lmspos + (m - 1u - (uint32_t)i)));
+    }
+};
+struct LmsValDesc {
+    const uint32_t *lmspos; uint32_t m;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return __ldg(lmspos + (m - 1u - (uint32_t)i)); }
+};
+
+// ---- round 1: groups of equal window keys in the sorted list (slot = index)
+struct InLmsGroup1 {
+    const uint32_t *K, *P; uint32_t m, n, span;      // span = h + kc: truncated <=> p + span > n
+    __device__ __forceinline__ bool trunc(uint32_t p) const { return (uint64_t)p + span > n; }
+    __device__ __forceinline__ bool head(uint32_t i) const {
+        return i == 0 || K[i] != K[i - 1] || trunc(P[i - 1]) || trunc(P[i]);
+    }
+    __device__ unsigned long long operator()(uint64_t ii) const {
+        uint32_t i = (uint32_t)ii;
+        bool hd = head(i), tl = (i + 1 == m) || head(i + 1);
+        return ((unsigned long long)(hd ? i : 0u) << 32) | ((hd && tl) ? 0u : 1u);
+    }
+};
+struct OutLmsCompact1 {
+    const uint32_t *P; uint32_t *aslot, *apos, *agrp;
+    __device__ void operator()(uint64_t i, unsigned long long exc, unsigned long long v) const {
+        if ((uint32_t)v) {
+            uint32_t eh = (uint32_t)(exc >> 32), vh = (uint32_t)(v >> 32), k = (uint32_t)exc;
+            aslot[k] = (uint32_t)i; apos[k] = P[i]; agrp[k] = eh > vh ? eh : vh;
+        }
+    }
+};
+
+// ---- round r >= 2 over the compacted active list (slot order; groups contiguous)
+template <int BITS>
+__global__ void __launch_bounds__(BLK) k_lms_refine_keys(LmsWin W, const uint32_t *__restrict__ apos,
+                                                         const uint32_t *__restrict__ agrp, uint32_t na, uint32_t h,
+                                                         uint64_t *keys) {
+    uint32_t j = blockIdx.x * BLK + threadIdx.x;
+    if (j >= na) return;
+    keys[j] = ((uint64_t)agrp[j] << 32) | lms_window<BITS>(W, apos[j] + h);    // apos + h <= n (not truncated before)
+}
+struct InLmsGroupR {
+    const uint64_t *K; const uint32_t *P, *slot; uint32_t na, n, span;
+    __device__ __forceinline__ bool trunc(uint32_t p) const { return (uint64_t)p + span > n; }
+    __device__ __forceinline__ bool head(uint32_t j) const {
+        return j == 0 || K[j] != K[j - 1] || trunc(P[j - 1]) || trunc(P[j]);
+    }
+    __device__ unsigned long long operator()(uint64_t jj) const {
+        uint32_t j = (uint32_t)jj;
+        bool hd = head(j), tl = (j + 1 == na) || head(j + 1);
+        return ((unsigned long long)(hd ? slot[j] : 0u) << 32) | ((hd && tl) ? 0u : 1u);
+    }
+};
+struct OutLmsCompactR {
+    const uint32_t *P, *slot; uint32_t *list; uint32_t *oslot, *opos, *ogrp;
+    __device__ void operator()(uint64_t j, unsigned long long exc, unsigned long long v) const {
+        uint32_t p = P[j], sl = slot[j];
+        list[sl] = p;                                   // position inside the group is final for this depth
+        if ((uint32_t)v) {
+            uint32_t eh = (uint32_t)(exc >> 32), vh = (uint32_t)(v >> 32), k = (uint32_t)exc;
+            oslot[k] = sl; opos[k] = p; ogrp[k] = eh > vh ? eh : vh;
+        }
+    }
+};
+
+}  // namespace b200sa

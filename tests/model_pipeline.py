@@ -351,8 +351,70 @@ def doubling_sa(R, kgram=None):
     return sa, rounds
 
 
-def build_sa(T, sigma=256, stats=None, multiround=0, paircount=False):
-    """Whole pipeline; T is a list/bytes of ints < sigma."""
+def lms_direct_sort(T, lmspos, kc, max_rounds=None, stats=None):
+    """Model of suffix_b200/csrc/lms_sort.cuh: LMS suffixes ordered by windows of kc
+    characters (zero-padded past the end of the text), first sort fed in DESCENDING
+    text position, every sort stable, truncated members (window runs past n) final
+    where the stable sort leaves them and forming groups of their own.  Returns the
+    LMS suffixes in suffix order, or None when max_rounds is exhausted."""
+    n = len(T)
+    codes = sorted(set(T))
+    code = {c: k for k, c in enumerate(codes)}            # dense, order preserving, 0-based
+
+    def window(p):                                        # p <= n
+        return tuple(code[T[p + i]] if p + i < n else 0 for i in range(kc))
+
+    items = list(reversed(lmspos))
+    lst = sorted(items, key=window)                       # Python's sort is stable
+    m = len(lst)
+
+    def groups(seq_keys, seq_pos, span):
+        """heads by the kernel's rule: key differs, or either neighbour truncated."""
+        heads = []
+        for j in range(len(seq_pos)):
+            tr = lambda p: p + span > n
+            heads.append(j == 0 or seq_keys[j] != seq_keys[j - 1] or tr(seq_pos[j - 1]) or tr(seq_pos[j]))
+        return heads
+
+    keys = [window(p) for p in lst]
+    heads = groups(keys, lst, kc)
+    # active = members of groups with more than one element: (slot, pos, grp)
+    def active_of(heads, slots, poss):
+        out = []
+        g = None
+        for j in range(len(poss)):
+            if heads[j]:
+                g = slots[j]
+            tail = (j + 1 == len(poss)) or heads[j + 1]
+            if not (heads[j] and tail):
+                out.append((slots[j], poss[j], g))
+        return out
+
+    act = active_of(heads, list(range(m)), lst)
+    h = kc
+    rounds = 1
+    while act:
+        if max_rounds is not None and rounds >= max_rounds:
+            return None
+        rounds += 1
+        slots = [a[0] for a in act]
+        ks = [(a[2], window(a[1] + h)) for a in act]      # a[1] + h <= n by the truncation rule
+        order = sorted(range(len(act)), key=lambda j: ks[j])
+        poss = [act[j][1] for j in order]
+        ks = [ks[j] for j in order]
+        for sl, p in zip(slots, poss):
+            lst[sl] = p
+        heads = groups(ks, poss, h + kc)
+        act = active_of(heads, slots, poss)
+        h += kc
+    if stats is not None:
+        stats["direct_rounds"] = rounds
+    return lst
+
+
+def build_sa(T, sigma=256, stats=None, multiround=0, paircount=False, direct_kc=0):
+    """Whole pipeline; T is a list/bytes of ints < sigma.  direct_kc > 0: the LMS suffixes are
+    sorted directly by character windows (lms_direct_sort) instead of stage-1 induce + naming."""
     T = list(T)
     n = len(T)
     if n == 0:
@@ -370,7 +432,12 @@ def build_sa(T, sigma=256, stats=None, multiround=0, paircount=False):
     for c in range(sigma):
         lms_off[c + 1] = lms_off[c] + lms_cnt[c]
     SA = [None] * n
-    if m > 0:
+    sorted_lms = None
+    if m > 0 and direct_kc:
+        sorted_lms = lms_direct_sort(T, lmspos, direct_kc, stats=stats)
+    if sorted_lms is not None:
+        pass
+    elif m > 0:
         # stage 1: LMS grouped by first char (stable counting sort, text order)
         grouped = sorted(lmspos, key=lambda p: T[p])
         if paircount:

@@ -71,8 +71,18 @@ def test_fixture_sha256(ctx, name):
     assert hashlib.sha256(lcp.astype("<u4").tobytes()).hexdigest() == info["lcp_sha256"]
 
 
+@pytest.fixture(params=["direct", "robust"])
+def lms_path(request, monkeypatch):
+    """Both ways of sorting the LMS suffixes: directly by character windows
+    (lms_sort.cuh; falls through to the robust path by itself on long repeats) and the
+    robust path alone (stage-1 induce + naming + rank doubling)."""
+    if request.param == "robust":
+        monkeypatch.setenv("B200SA_NO_DIRECT", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("name,data", families.adversarial(), ids=lambda x: x if isinstance(x, str) else "")
-def test_adversarial(ctx, name, data):
+def test_adversarial(ctx, lms_path, name, data):
     t = _np(data)
     want = oracle.sais(t)
     sa, lcp = ctx.build_lcp(t)
@@ -83,7 +93,7 @@ def test_adversarial(ctx, name, data):
 @pytest.mark.parametrize("maker,n", [("dna", 1_000_000), ("dna_nl", 1_000_001), ("bytes", 1_000_000),
                                      ("english", 1_000_000), ("tiled", 1_000_000), ("dna", 5_000_000),
                                      ("bytes", 5_000_000)])
-def test_medium_vs_oracle(ctx, maker, n):
+def test_medium_vs_oracle(ctx, lms_path, maker, n):
     if maker == "dna":
         t = gen.dna(n)
     elif maker == "dna_nl":
@@ -139,7 +149,7 @@ def _long_run_cases():
 
 
 @pytest.mark.parametrize("name,t", _long_run_cases(), ids=lambda x: x if isinstance(x, str) else "")
-def test_long_runs(ctx, name, t):
+def test_long_runs(ctx, lms_path, name, t):
     """Run skipping in the induce: chains along runs of 10^5..10^6 equal bytes."""
     t = np.ascontiguousarray(t)
     sa = ctx.build(t)
@@ -258,6 +268,27 @@ def test_positions_dev_batch(ctx):
     for k, q in enumerate(queries):
         assert (int(s[k]), int(e[k])) == oracle.positions(t, tab.table(), q), q     # src/table.rs:223-259
         assert tab.table()[s[k]:e[k]].tolist() == tab.positions(q).tolist(), q
+
+
+def test_direct_path_taken(ctx):
+    """The direct LMS sort must actually be the path random-like texts take (and the
+    robust path the one a tiled text ends up on)."""
+    ctx.build(gen.dna(2_000_000))
+    assert ctx.stats()["direct_sort"] == 1
+    ctx.build(gen.rand_bytes(2_000_000))
+    assert ctx.stats()["direct_sort"] == 1
+    ctx.build(gen.dna(2_000_001, newline_tail=True))
+    assert ctx.stats()["direct_sort"] == 1
+    ctx.build(gen.tiled(gen.fixture("AP009048_10000.fasta"), 2_000_000))
+    assert ctx.stats()["direct_sort"] == 0
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 3])
+def test_direct_round_limits(ctx, monkeypatch, rounds):
+    """Giving up after any number of window rounds hands over to the robust path cleanly."""
+    monkeypatch.setenv("B200SA_DIRECT_ROUNDS", str(rounds))
+    for t in (gen.fixture("AP009048_100000.fasta"), gen.english(400_000), gen.dna(500_000)):
+        assert np.array_equal(ctx.build(t), oracle.sais(t))
 
 
 def test_build_dev_matches_host(ctx):

@@ -63,3 +63,25 @@ def test_model_paircount_induce(name, data):
 @given(st.binary(max_size=100))
 def test_model_paircount_prop(t):
     assert mp.build_sa(t, paircount=True) == oracle.naive_sa(t).tolist()
+
+
+@pytest.mark.parametrize("kc", [1, 2, 3, 16])
+@pytest.mark.parametrize("name,data", families.adversarial(), ids=lambda x: x if isinstance(x, str) else "")
+def test_model_direct_lms_sort(name, data, kc):
+    """Direct LMS-suffix sort by character windows (suffix_b200/csrc/lms_sort.cuh): descending
+    feed + stable sorts + truncated-members-are-final give the suffix order without a sentinel."""
+    data = data[:1500]
+    assert mp.build_sa(data, direct_kc=kc) == oracle.sais(data).tolist()
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.text(alphabet="ab\x00", max_size=60), st.integers(1, 5))
+def test_model_direct_lms_sort_prop(s, kc):
+    t = s.encode()
+    assert mp.build_sa(t, direct_kc=kc) == oracle.naive_sa(t).tolist()
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.binary(max_size=80), st.integers(1, 4))
+def test_model_direct_lms_sort_prop_binary(t, kc):
+    assert mp.build_sa(t, direct_kc=kc) == oracle.naive_sa(t).tolist()
