@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "classify.cuh"
 #include "induce.cuh"
+#include "induce2.cuh"
 #include "pipeline_kernels.cuh"
 #include "lms_sort.cuh"
 
@@ -64,6 +65,8 @@ struct b200sa_ctx {
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
     DevBuf packed, scan_state;
     uint32_t scan_epoch = 0, scan_tiles_cap = 0;
+    bool l2_persist = false;          // access policy window for the packed text (B200SA_L2PERSIST)
+    size_t l2_max_window = 0, l2_set_aside = 0;
     uint32_t sigma = 256;            // distinct bytes of the current text
     int bits = 8;                    // bits per char of the packed text of the current call (2, 4 or 8 = raw)
     const void *ptext = nullptr;     // packed words, or the byte text when bits == 8
@@ -129,7 +132,9 @@ static void begin_call(b200sa_ctx *c, void *stream) {
     c->launches = 0;
     c->last_error.clear();
 }
+static void l2_window(b200sa_ctx *c, const void *p, size_t bytes);
 static int end_call(b200sa_ctx *c) {
+    if (c->l2_persist) l2_window(c, nullptr, 0);              // the caller's stream leaves without our policy
     c->stats.kernel_launches = c->launches;
     c->stats.workspace_bytes = c->ws_bytes;
     c->phase_names.clear();
@@ -431,6 +436,22 @@ static int reduced_sa(b200sa_ctx *c, uint32_t *R, uint32_t m, uint32_t names, ui
     return B200SA_OK;
 }
 
+// ------------------------------------------------------- L2 residency of the packed text
+// The induce, the window keys of the LMS sort and the direct LCP all gather from the packed
+// text at random while hundreds of MB of suffix-array data stream through L2.  An access
+// policy window marks the packed text persisting (evict-last) for the kernels of this call.
+static void l2_window(b200sa_ctx *c, const void *p, size_t bytes) {
+    if (!c->l2_persist || c->l2_max_window == 0) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    v.accessPolicyWindow.base_ptr = const_cast<void *>(p);
+    v.accessPolicyWindow.num_bytes = bytes < c->l2_max_window ? bytes : c->l2_max_window;
+    v.accessPolicyWindow.hitRatio = bytes ? 1.0f : 0.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+}
+
 // ------------------------------------------------------- packed text
 // Chooses 2 / 4 bits per char when the alphabet allows it and packs the text;
 // code_of/alpha live in the tables buffer.
@@ -448,6 +469,7 @@ static int pack_text(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t si
     else LAUNCH(c, (k_pack<4>), cdiv(words, BLK), text, n, tab + T_CODE, ptr<uint32_t>(c->packed));
     CU_TRY(c, cudaGetLastError());
     c->ptext = c->packed.p;
+    if (words * 4 <= c->l2_set_aside) l2_window(c, c->packed.p, words * 4 + 8);
     return B200SA_OK;
 }
 
@@ -498,7 +520,16 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
     uint32_t *grpA = ptr<uint32_t>(c->g0), *grpB = ptr<uint32_t>(c->g1);
     uint32_t *posA = ptr<uint32_t>(c->sa_r), *posB = ptr<uint32_t>(c->rank);
     unsigned long long *d_tot = reinterpret_cast<unsigned long long *>(sm + 16);
-    TRY((dev_scan<OpMaxSum>(c, InLmsGroup1{Ks, Ps, m, n, kc}, OutLmsCompact1{Ps, slotA, posA, grpA}, m, d_tot)));
+    {
+        size_t fw = ((size_t)m + 31) / 32 + 1;
+        TRY(ensure(c, c->flag, fw * 4));
+        uint32_t *forced = ptr<uint32_t>(c->flag);
+        CU_TRY(c, cudaMemsetAsync(forced, 0, fw * 4, c->stream));
+        CU_TRY(c, cudaMemsetAsync(sm + 16, 0, 8, c->stream));
+        LAUNCH(c, (k_lms_mark_trunc<BITS>), 1u, W, ptr<uint32_t>(c->lmspos), m, Ks, Ps, kc, forced);
+        InLmsActive1 in1{Ks, forced, m};
+        TRY((dev_scan<OpSum>(c, in1, OutLmsCompact1{in1, Ps, slotA, posA, grpA}, m, sm + 16)));
+    }
     TRY(read_words(c, sm + 16, 1));
     uint32_t na = c->h_pin[0];
     c->stats.names = m - na;                       // LMS suffixes settled by the first window
@@ -506,7 +537,10 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
     uint32_t max_rounds = 6;
     if (const char *e = getenv("B200SA_DIRECT_ROUNDS")) { int v = atoi(e); if (v >= 1) max_rounds = (uint32_t)v; }
     if (getenv("B200SA_TRACE")) fprintf(stderr, "[b200sa] direct LMS sort: kc=%u, round 1 leaves %u of %u tied\n", kc, na, m);
-    if ((uint64_t)na * 10 > (uint64_t)m * 9 && m > 64) return B200SA_OK;   // the window tells nothing apart: long repeats
+    const bool force = getenv("B200SA_DIRECT_FORCE") != nullptr;            // experiments: never bail out early
+    if (!force && (uint64_t)na * 10 > (uint64_t)m * 9 && m > 64) return B200SA_OK;   // the window tells nothing apart
+    if (na > 0)     // group id of every tied element = slot of its group's head
+        TRY((dev_scan<OpMax>(c, InArray{grpA}, OutMaxInPlace{grpA}, na, nullptr)));
     uint64_t h = kc;
     bool try_local = getenv("B200SA_NO_LOCAL_SORT") == nullptr;
     const int gbits = 32 + bit_length(m);
@@ -544,7 +578,7 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
         uint32_t na_next = c->h_pin[0];
         if (getenv("B200SA_TRACE")) fprintf(stderr, "[b200sa] direct LMS sort: round %u (h=%llu): %u -> %u tied\n", rounds, (unsigned long long)h, na, na_next);
         // slow convergence on a large residue means long repeats: stop early
-        if (rounds >= 3 && (uint64_t)na_next * 2 > na && (uint64_t)na_next * 64 > m) return B200SA_OK;
+        if (!force && rounds >= 3 && (uint64_t)na_next * 2 > na && (uint64_t)na_next * 64 > m) return B200SA_OK;
         na = na_next;
         uint32_t *t;
         t = slotA; slotA = slotB; slotB = t;
@@ -565,6 +599,10 @@ static int lms_direct_sort(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **lis
 
 // ------------------------------------------------------- induce launcher
 static const void *induce_fn(bool spass, int bits) {
+    // packed text: multi-round bucket steps (induce2.cuh); B200SA_INDUCE_V1 keeps the one-round kernel
+    static const bool v1 = getenv("B200SA_INDUCE_V1") != nullptr;
+    if (bits == 2 && !v1) return spass ? (const void *)k_induce2<true, 2> : (const void *)k_induce2<false, 2>;
+    if (bits == 4 && !v1) return spass ? (const void *)k_induce2<true, 4> : (const void *)k_induce2<false, 4>;
     if (bits == 2) return spass ? (const void *)k_induce<true, 2> : (const void *)k_induce<false, 2>;
     if (bits == 4) return spass ? (const void *)k_induce<true, 4> : (const void *)k_induce<false, 4>;
     return spass ? (const void *)k_induce<true, 8> : (const void *)k_induce<false, 8>;
@@ -947,6 +985,18 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
         if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
     }
     if (!prop.cooperativeLaunch) { delete c; return B200SA_ERR_NO_DEVICE; }
+    if (const char *e = getenv("B200SA_L2PERSIST")) {
+        int mb = atoi(e);                                       // MB of L2 set aside for persisting lines
+        if (mb > 0 && prop.persistingL2CacheMaxSize > 0) {
+            size_t want = (size_t)mb << 20;
+            if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                c->l2_persist = true;
+                c->l2_set_aside = want;
+                c->l2_max_window = (size_t)prop.accessPolicyMaxWindowSize;
+            } else cudaGetLastError();
+        }
+    }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200SA_ERR_CUDA; }
     c->stream = c->own_stream;
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -403,6 +403,70 @@ __device__ __noinline__ void induce_run_skip(const InduceArgs &A, IndShared &sh,
     __syncthreads();
 }
 
+// ---------------- small episode: block 0 alone consumes consecutive small steps (lists of at
+// most TILE entries, one chain round per step, run skipping for long runs) and then hands
+// its fill counters / state to the grid; the other blocks serve grid-wide emission
+// requests of the run skipping while they wait.  All blocks call this with sh.has set
+// and sh.seg.len <= TILE.
+template <bool SPASS, int BITS>
+__device__ __noinline__ void induce_small_episode(const InduceArgs &A, IndShared &sh, cg::grid_group &grid,
+                                                  uint32_t &smallcount) {
+    const uint32_t bid = blockIdx.x, tid = threadIdx.x;
+    if (bid == 0) {
+        while (sh.has && sh.seg.len <= (uint32_t)TILE) {
+            Seg g = sh.seg;
+            smallcount++;
+            const bool chain = sh.is_chain != 0;
+            const int32_t cc = sh.ns_c;                 // a chain segment keeps ns_c == its bucket
+            __syncthreads();
+            if (tid == 0) {
+                if (chain && sh.streak_c == cc) sh.streak++;
+                else { sh.streak = chain ? 1u : 0u; sh.streak_c = chain ? cc : -1; }
+            }
+            __syncthreads();
+            if (chain && sh.streak >= RUN_STREAK) {
+                induce_run_skip<SPASS, BITS>(A, sh, g, (uint32_t)cc, grid);
+                if (tid == 0) { sh.st_c = cc; sh.st_phase = 0; sh.st_begin = sh.fill[cc]; sh.streak = 0; sh.streak_c = -1; }
+                __syncthreads();
+                if (tid == 0) induce_peek<SPASS>(A, sh);
+                __syncthreads();
+                continue;
+            }
+            sh.base[tid] = sh.fill[tid];
+            __syncthreads();
+            induce_tile<SPASS, MODE_SMALL, BITS>(A, sh, g, 0);
+            sh.fill[tid] = sh.base[tid];
+            if (tid == 0) { sh.st_c = sh.ns_c; sh.st_phase = sh.ns_phase; sh.st_begin = sh.ns_begin; }
+            __syncthreads();
+            if (tid == 0) induce_peek<SPASS>(A, sh);
+            __syncthreads();
+        }
+        A.g_fill[tid] = sh.fill[tid];
+        if (tid == 0) {
+            A.g_state[0] = sh.st_c; A.g_state[1] = sh.st_phase; A.g_state[2] = (int32_t)sh.st_begin;
+            A.cmd[0] = CMD_DONE;
+        }
+        __threadfence();
+        grid.sync();
+    } else {
+        // wait for block 0; serve grid-wide emission requests of its run skipping meanwhile
+        while (true) {
+            grid.sync();
+            if (__ldcg(A.cmd + 0) != CMD_EMIT) break;
+            grid_emit<SPASS>(A, sh);
+            grid.sync();
+        }
+    }
+    if (bid != 0) {
+        sh.fill[tid] = __ldcg(A.g_fill + tid);
+        if (tid == 0) {
+            sh.st_c = __ldcg(A.g_state + 0); sh.st_phase = __ldcg(A.g_state + 1);
+            sh.st_begin = (uint32_t)__ldcg(A.g_state + 2);
+        }
+    }
+    __syncthreads();
+}
+
 #ifndef INDUCE_MINB
 #define INDUCE_MINB 2
 #endif
@@ -431,60 +495,7 @@ __global__ void __launch_bounds__(BLK, INDUCE_MINB) k_induce(InduceArgs A) {
         __syncthreads();
         if (!sh.has) break;
         if (sh.seg.len <= (uint32_t)TILE) {
-            // ---------------- small episode: block 0 alone
-            if (bid == 0) {
-                while (sh.has && sh.seg.len <= (uint32_t)TILE) {
-                    Seg g = sh.seg;
-                    smallcount++;
-                    const bool chain = sh.is_chain != 0;
-                    const int32_t cc = sh.ns_c;                 // a chain segment keeps ns_c == its bucket
-                    __syncthreads();
-                    if (tid == 0) {
-                        if (chain && sh.streak_c == cc) sh.streak++;
-                        else { sh.streak = chain ? 1u : 0u; sh.streak_c = chain ? cc : -1; }
-                    }
-                    __syncthreads();
-                    if (chain && sh.streak >= RUN_STREAK) {
-                        induce_run_skip<SPASS, BITS>(A, sh, g, (uint32_t)cc, grid);
-                        if (tid == 0) { sh.st_c = cc; sh.st_phase = 0; sh.st_begin = sh.fill[cc]; sh.streak = 0; sh.streak_c = -1; }
-                        __syncthreads();
-                        if (tid == 0) induce_peek<SPASS>(A, sh);
-                        __syncthreads();
-                        continue;
-                    }
-                    sh.base[tid] = sh.fill[tid];
-                    __syncthreads();
-                    induce_tile<SPASS, MODE_SMALL, BITS>(A, sh, g, 0);
-                    sh.fill[tid] = sh.base[tid];
-                    if (tid == 0) { sh.st_c = sh.ns_c; sh.st_phase = sh.ns_phase; sh.st_begin = sh.ns_begin; }
-                    __syncthreads();
-                    if (tid == 0) induce_peek<SPASS>(A, sh);
-                    __syncthreads();
-                }
-                A.g_fill[tid] = sh.fill[tid];
-                if (tid == 0) {
-                    A.g_state[0] = sh.st_c; A.g_state[1] = sh.st_phase; A.g_state[2] = (int32_t)sh.st_begin;
-                    A.cmd[0] = CMD_DONE;
-                }
-                __threadfence();
-                grid.sync();
-            } else {
-                // wait for block 0; serve grid-wide emission requests of its run skipping meanwhile
-                while (true) {
-                    grid.sync();
-                    if (__ldcg(A.cmd + 0) != CMD_EMIT) break;
-                    grid_emit<SPASS>(A, sh);
-                    grid.sync();
-                }
-            }
-            if (bid != 0) {
-                sh.fill[tid] = __ldcg(A.g_fill + tid);
-                if (tid == 0) {
-                    sh.st_c = __ldcg(A.g_state + 0); sh.st_phase = __ldcg(A.g_state + 1);
-                    sh.st_begin = (uint32_t)__ldcg(A.g_state + 2);
-                }
-            }
-            __syncthreads();
+            induce_small_episode<SPASS, BITS>(A, sh, grid, smallcount);
             continue;
         }
         // -------------------- big step: all blocks

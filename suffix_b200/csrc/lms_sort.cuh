@@ -92,27 +92,56 @@ struct LmsValDesc {
     __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return __ldg(lmspos + (m - 1u - (uint32_t)i)); }
 };
 
-// ---- round 1: groups of equal window keys in the sorted list (slot = index)
-struct InLmsGroup1 {
-    const uint32_t *K, *P; uint32_t m, n, span;      // span = h + kc: truncated <=> p + span > n
-    __device__ __forceinline__ bool trunc(uint32_t p) const { return (uint64_t)p + span > n; }
-    __device__ __forceinline__ bool head(uint32_t i) const {
-        return i == 0 || K[i] != K[i - 1] || trunc(P[i - 1]) || trunc(P[i]);
+// ---- round 1: groups of equal window keys in the sorted list (slot = index).
+// Only LMS positions inside the last `span` characters can be truncated (at most span/2
+// of them, the last entries of lmspos).  One small kernel finds their slots -- they
+// stand at the very start of their run of equal keys, in descending position -- and
+// sets "forced head" bits for the slot and its successor, so that the scan over all m
+// elements reads the keys only.
+template <int BITS>
+__global__ void __launch_bounds__(BLK) k_lms_mark_trunc(LmsWin W, const uint32_t *__restrict__ lmspos, uint32_t m,
+                                                        const uint32_t *__restrict__ K, const uint32_t *__restrict__ P,
+                                                        uint32_t span, uint32_t *forced) {
+    uint32_t t = threadIdx.x;
+    if (t >= m || t >= span) return;
+    uint32_t p = lmspos[m - 1u - t];
+    if ((uint64_t)p + span <= W.n) return;                // not truncated
+    uint32_t key = lms_window<BITS>(W, p);
+    uint32_t lo = 0, hi = m;
+    while (lo < hi) {                                     // first slot with K >= key
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (K[mid] < key) lo = mid + 1; else hi = mid;
     }
-    __device__ unsigned long long operator()(uint64_t ii) const {
-        uint32_t i = (uint32_t)ii;
-        bool hd = head(i), tl = (i + 1 == m) || head(i + 1);
-        return ((unsigned long long)(hd ? i : 0u) << 32) | ((hd && tl) ? 0u : 1u);
-    }
-};
-struct OutLmsCompact1 {
-    const uint32_t *P; uint32_t *aslot, *apos, *agrp;
-    __device__ void operator()(uint64_t i, unsigned long long exc, unsigned long long v) const {
-        if ((uint32_t)v) {
-            uint32_t eh = (uint32_t)(exc >> 32), vh = (uint32_t)(v >> 32), k = (uint32_t)exc;
-            aslot[k] = (uint32_t)i; apos[k] = P[i]; agrp[k] = eh > vh ? eh : vh;
+    for (uint32_t j = lo; j < m && K[j] == key; j++) {
+        if (P[j] == p) {
+            atomicOr(&forced[j >> 5], 1u << (j & 31));
+            if (j + 1 < m) atomicOr(&forced[(j + 1) >> 5], 1u << ((j + 1) & 31));
+            break;
         }
     }
+}
+struct InLmsActive1 {
+    const uint32_t *K, *forced; uint32_t m;
+    __device__ __forceinline__ bool head(uint32_t i) const {
+        return i == 0 || K[i] != K[i - 1] || ((forced[i >> 5] >> (i & 31)) & 1u);
+    }
+    __device__ uint32_t operator()(uint64_t ii) const {
+        uint32_t i = (uint32_t)ii;
+        bool hd = head(i), tl = (i + 1 == m) || head(i + 1);
+        return (hd && tl) ? 0u : 1u;
+    }
+};
+// compaction of the tied elements; ahead[k] = slot if the element starts its group, else 0
+// (a max-scan over the compacted list turns it into the group id)
+struct OutLmsCompact1 {
+    InLmsActive1 in; const uint32_t *P; uint32_t *aslot, *apos, *ahead;
+    __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const {
+        if (v) { aslot[exc] = (uint32_t)i; apos[exc] = P[i]; ahead[exc] = in.head((uint32_t)i) ? (uint32_t)i : 0u; }
+    }
+};
+struct OutMaxInPlace {
+    uint32_t *a;
+    __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const { a[i] = exc > v ? exc : v; }
 };
 
 // ---- round r >= 2 over the compacted active list (slot order; groups contiguous)

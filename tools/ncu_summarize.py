@@ -54,10 +54,27 @@ def full(rep, out):
     idx = {w: hdr.index(w) for w in WANT if w in hdr}
     kn = hdr.index("Kernel Name")
     res = []
+    stall_cols = [(i, h) for i, h in enumerate(hdr) if "issue_stalled" in h and h.endswith("per_warp_active.pct")]
+    extra = [h for h in hdr if h in ("lts__throughput.avg.pct_of_peak_sustained_elapsed",
+                                     "l1tex__throughput.avg.pct_of_peak_sustained_active",
+                                     "sm__inst_executed.sum", "smsp__inst_executed.avg.per_cycle_active",
+                                     "lts__t_bytes.sum", "l1tex__t_bytes.sum", "sm__cycles_active.avg",
+                                     "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+                                     "launch__waves_per_multiprocessor", "sm__maximum_warps_per_active_cycle_pct")]
     for row in r[2:]:
         d = {"kernel": row[kn]}
         for w, i in idx.items():
             d[w] = "%s %s" % (row[i], units[i])
+        for h in extra:
+            d[h] = "%s %s" % (row[hdr.index(h)], units[hdr.index(h)])
+        st = []
+        for i, h in stall_cols:
+            try:
+                st.append((float(row[i].replace(",", "")), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_warp_active.pct", "")))
+            except ValueError:
+                pass
+        st.sort(reverse=True)
+        d["top_stalls_pct_of_warp_active"] = {nm: v for v, nm in st[:6]}
         res.append(d)
     with open(out, "w") as f:
         json.dump({"source": rep, "launches": res}, f, indent=1)

@@ -38,9 +38,18 @@ def run(ctx, name, t, reps=2, lcp=True):
 
 
 if __name__ == "__main__":
-    sizes = [int(x) for x in sys.argv[1:]] or [1_000_000, 10_000_000, 100_000_000]
+    kinds = ["dna", "dna_nl", "bytes", "english"]
+    args = []
+    for a in sys.argv[1:]:
+        if a.startswith("--kinds="):
+            kinds = a.split("=", 1)[1].split(",")
+        else:
+            args.append(a)
+    sizes = [int(x) for x in args] or [1_000_000, 10_000_000, 100_000_000]
     ctx = _lib.Context(0)
+    makers = {"dna": lambda n: gen.dna(n), "dna_nl": lambda n: gen.dna(n, newline_tail=True),
+              "bytes": lambda n: gen.rand_bytes(n), "english": lambda n: gen.english(n),
+              "tiled": lambda n: gen.tiled(gen.fixture("AP009048_100000.fasta"), n)}
     for n in sizes:
-        run(ctx, "dna", gen.dna(n))
-        run(ctx, "bytes", gen.rand_bytes(n))
-    run(ctx, "english_10M", gen.english(10_000_000))
+        for k in kinds:
+            run(ctx, k, makers[k](n))
