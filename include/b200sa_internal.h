@@ -23,6 +23,12 @@ int b200sa_test_classify(b200sa_ctx *ctx, const uint8_t *text, uint64_t n,
                          uint32_t *stype_words, uint32_t *lms_words, uint32_t *hist768,
                          uint32_t *lmspos, uint64_t cap_lms, uint64_t *m_out);
 
+/* The same through the fused single-pass classifier (classify2.cuh): lmspos_desc holds the
+ * LMS positions in DESCENDING text order (the order the LMS sort is fed in). */
+int b200sa_test_classify_fused(b200sa_ctx *ctx, const uint8_t *text, uint64_t n,
+                               uint32_t *stype_words, uint32_t *lms_words, uint32_t *hist768,
+                               uint32_t *lmspos_desc, uint64_t cap_lms, uint64_t *m_out);
+
 /* Generic scan: op 0 = exclusive sum, op 1 = exclusive max; *total = reduction. */
 int b200sa_test_scan(b200sa_ctx *ctx, const uint32_t *in, uint64_t n, int op,
                      uint32_t *out_excl, uint32_t *total);

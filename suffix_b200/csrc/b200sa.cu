@@ -18,8 +18,10 @@
 #include "../../include/b200sa_internal.h"
 #include "common.cuh"
 #include "classify.cuh"
+#include "classify2.cuh"
 #include "induce.cuh"
 #include "induce2.cuh"
+#include "induce3.cuh"
 #include "pipeline_kernels.cuh"
 #include "lms_sort.cuh"
 
@@ -40,7 +42,8 @@ struct b200sa_ctx {
     int sm_count = 0;
     int induce_blocks = 0;          // largest co-resident grid (workspace is sized for it)
     int induce_bps_max = 1;         // occupancy bound over all variants, blocks per SM
-    int induce_occ[3] = {1, 1, 1};  // occupancy bound per text packing (2, 4, 8 bits)
+    int induce_occ[3] = {1, 1, 1};  // occupancy bound per text packing (2, 4, 8 bits) of the default variant
+    int induce_occ_v[4][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}};   // per kernel variant
     int induce_bps_env = 0;         // B200SA_INDUCE_BPS override (0 = adaptive)
     int cur_induce_blocks = 0;      // grid of the current build
     std::string last_error;
@@ -63,7 +66,9 @@ struct b200sa_ctx {
     DevBuf blkstate, carry, tables, small, scan_partial, radix_cnt, blkcnt;
     DevBuf os_hist, os_status, phik, phiv, runscr, plcp_samp;
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
-    DevBuf packed, scan_state;
+    DevBuf packed, scan_state, cls_state, lmsdesc, steplog;
+    uint32_t cls_calls = 0;
+    bool lms_asc_ready = false;       // c->lmspos / c->lmsrank (text order) valid for the current text
     uint32_t scan_epoch = 0, scan_tiles_cap = 0;
     bool l2_persist = false;          // access policy window for the packed text (B200SA_L2PERSIST)
     size_t l2_max_window = 0, l2_set_aside = 0;
@@ -505,8 +510,8 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
     uint32_t *sm = ptr<uint32_t>(c->small);
     uint32_t *Ks, *Ps;
     TRY(mark(c, "lms_sort"));
-    TRY((sort_pairs_from<uint32_t>(c, LmsKeyDesc<BITS>{W, ptr<uint32_t>(c->lmspos), m},
-                                   LmsValDesc{ptr<uint32_t>(c->lmspos), m}, ptr<uint32_t>(c->k32b), ptr<uint32_t>(c->v0),
+    TRY((sort_pairs_from<uint32_t>(c, LmsKeyDesc<BITS>{W, ptr<uint32_t>(c->lmsdesc)},
+                                   LmsValDesc{ptr<uint32_t>(c->lmsdesc)}, ptr<uint32_t>(c->k32b), ptr<uint32_t>(c->v0),
                                    ptr<uint32_t>(c->reduced), ptr<uint32_t>(c->v1), m, bit_length(range - 1), &Ks, &Ps)));
     // groups of equal windows; members of non-singleton groups -> active list
     TRY(mark(c, "lms_groups"));
@@ -526,7 +531,7 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
         uint32_t *forced = ptr<uint32_t>(c->flag);
         CU_TRY(c, cudaMemsetAsync(forced, 0, fw * 4, c->stream));
         CU_TRY(c, cudaMemsetAsync(sm + 16, 0, 8, c->stream));
-        LAUNCH(c, (k_lms_mark_trunc<BITS>), 1u, W, ptr<uint32_t>(c->lmspos), m, Ks, Ps, kc, forced);
+        LAUNCH(c, (k_lms_mark_trunc<BITS>), 1u, W, ptr<uint32_t>(c->lmsdesc), m, Ks, Ps, kc, forced);
         InLmsActive1 in1{Ks, forced, m};
         TRY((dev_scan<OpSum>(c, in1, OutLmsCompact1{in1, Ps, slotA, posA, grpA}, m, sm + 16)));
     }
@@ -598,11 +603,24 @@ static int lms_direct_sort(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **lis
 }
 
 // ------------------------------------------------------- induce launcher
-static const void *induce_fn(bool spass, int bits) {
-    // packed text: multi-round bucket steps (induce2.cuh); B200SA_INDUCE_V1 keeps the one-round kernel
-    static const bool v1 = getenv("B200SA_INDUCE_V1") != nullptr;
-    if (bits == 2 && !v1) return spass ? (const void *)k_induce2<true, 2> : (const void *)k_induce2<false, 2>;
-    if (bits == 4 && !v1) return spass ? (const void *)k_induce2<true, 4> : (const void *)k_induce2<false, 4>;
+// Kernel variants of the induce passes: 1 = one-round steps with MATCH ranking (any packing),
+// 2 = multi-round bucket steps (packed text), 3 = packed-counter ranking (2-bit text only).
+static int induce_variant_env() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("B200SA_INDUCE"); v = e ? atoi(e) : 0; }
+    return v;
+}
+static int induce_variant(int bits) {
+    int v = induce_variant_env();
+    if (v == 2 && bits < 8) return 2;
+    if (v == 1) return 1;
+    if (bits == 2) return 3;
+    return 1;
+}
+static const void *induce_fn_v(bool spass, int bits, int variant) {
+    if (variant == 3 && bits == 2) return spass ? (const void *)k_induce3<true> : (const void *)k_induce3<false>;
+    if (variant == 2 && bits == 2) return spass ? (const void *)k_induce2<true, 2> : (const void *)k_induce2<false, 2>;
+    if (variant == 2 && bits == 4) return spass ? (const void *)k_induce2<true, 4> : (const void *)k_induce2<false, 4>;
     if (bits == 2) return spass ? (const void *)k_induce<true, 2> : (const void *)k_induce<false, 2>;
     if (bits == 4) return spass ? (const void *)k_induce<true, 4> : (const void *)k_induce<false, 4>;
     return spass ? (const void *)k_induce<true, 8> : (const void *)k_induce<false, 8>;
@@ -622,13 +640,105 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
     A.run_scratch = ptr<uint32_t>(c->runscr);
     A.run_alive = A.run_scratch + TILE;
     A.cmd = sm + 336;
+    A.steplog = nullptr;
+    if (getenv("B200SA_STEPLOG")) {
+        if (ensure(c, c->steplog, 4096 * 8) == B200SA_OK) {
+            A.steplog = ptr<unsigned long long>(c->steplog);
+            if (!spass) cudaMemsetAsync(c->steplog.p, 0, 8, c->stream);
+        }
+    }
     void *args[] = {&A};
-    CU_TRY(c, cudaLaunchCooperativeKernel(induce_fn(spass, c->bits), dim3(c->cur_induce_blocks), dim3(BLK), args, 0, c->stream));
+    int variant = induce_variant(c->bits);
+    if (variant == 3 && (((uintptr_t)sa | (uintptr_t)lms) & 15) != 0) variant = 1;      // 16-byte loads need aligned arrays
+    int bi = c->bits == 2 ? 0 : (c->bits == 4 ? 1 : 2);
+    int blocks = c->cur_induce_blocks, cap = c->sm_count * c->induce_occ_v[variant][bi];
+    if (blocks > cap) blocks = cap;
+    CU_TRY(c, cudaLaunchCooperativeKernel(induce_fn_v(spass, c->bits, variant), dim3(blocks), dim3(BLK), args, 0, c->stream));
     c->launches++;
     return B200SA_OK;
 }
 
 // ------------------------------------------------------- the level driver
+// After the histogram is known: packed text and the grid of the persistent induce kernels.
+static int post_classify(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t sigma) {
+    TRY(pack_text(c, text, n, sigma));
+    // few buckets -> long lists, latency bound -> more blocks per SM; many buckets -> grid-sync bound -> one per SM
+    int bps = sigma <= 16 ? 3 : (sigma <= 64 ? 2 : 1);
+    if (c->induce_bps_env) bps = c->induce_bps_env;
+    int occ_here = c->induce_occ[c->bits == 2 ? 0 : (c->bits == 4 ? 1 : 2)];
+    if (bps > occ_here) bps = occ_here;
+    if (bps < 1) bps = 1;
+    c->cur_induce_blocks = c->sm_count * bps;
+    return B200SA_OK;
+}
+
+// Scan descriptors for a kernel that embeds tile_lookback (same buffer and epochs as dev_scan).
+static int scan_state_for(b200sa_ctx *c, uint32_t nb, ScanState *S) {
+    size_t need = (size_t)nb * 20 + 64;
+    if (c->scan_state.cap < need) {
+        TRY(ensure(c, c->scan_state, need * 2));
+        CU_TRY(c, cudaMemsetAsync(c->scan_state.p, 0, c->scan_state.cap, c->stream));
+        c->scan_tiles_cap = (uint32_t)((c->scan_state.cap - 64) / 20);
+    }
+    uint8_t *basep = ptr<uint8_t>(c->scan_state);
+    S->ticket = reinterpret_cast<uint32_t *>(basep);
+    S->agg = reinterpret_cast<unsigned long long *>(basep + 64);
+    S->incl = S->agg + c->scan_tiles_cap;
+    S->flag = reinterpret_cast<uint32_t *>(S->incl + c->scan_tiles_cap);
+    c->scan_epoch += 2;
+    S->epoch = c->scan_epoch;
+    return B200SA_OK;
+}
+
+// K1 fused (classify2.cuh): one pass -> type / LMS bitmaps, (byte, type) histogram, bucket
+// tables, LMS positions in descending text order (c->lmsdesc), packed text.
+static int classify_fused_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *m_out) {
+    uint64_t nw = (n + 31) / 32;
+    uint32_t nbc = cdiv(nw, CLS_WORDS);
+    TRY(ensure(c, c->stype, nw * 4));
+    TRY(ensure(c, c->lmsb, nw * 4));
+    TRY(ensure(c, c->tables, T_END * 4));
+    TRY(ensure(c, c->small, 4096));
+    TRY(ensure(c, c->lmsdesc, (size_t)(n / 2 + 2) * 4));
+    if (c->cls_state.cap < (size_t)nbc * 4) {
+        TRY(ensure(c, c->cls_state, (size_t)nbc * 8));
+        CU_TRY(c, cudaMemsetAsync(c->cls_state.p, 0, c->cls_state.cap, c->stream));
+    }
+    uint32_t *tab = ptr<uint32_t>(c->tables), *hist = tab + T_HIST, *sm = ptr<uint32_t>(c->small);
+    CU_TRY(c, cudaMemsetAsync(hist, 0, 768 * 4, c->stream));
+    CU_TRY(c, cudaMemsetAsync(sm, 0, 4096, c->stream));
+    ScanState S;
+    TRY(scan_state_for(c, nbc, &S));
+    Cls2State CS{ptr<uint32_t>(c->cls_state), (++c->cls_calls) * 8u};
+    LAUNCH(c, k_classify_fused, nbc, text, n, nbc, S, CS, ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb), hist,
+           ptr<uint32_t>(c->lmsdesc), sm, ShardEdge{-1, -1, ST_L});
+    LAUNCH(c, k_bucket_tables, 1, hist, tab + T_BSTART, tab + T_LCNT, tab + T_SCNT, tab + T_LMSOFF, tab + T_CODE,
+           tab + T_ALPHA, sm + 3);
+    CU_TRY(c, cudaGetLastError());
+    if (c->early_sa_out)
+        CU_TRY(c, cudaMemcpyAsync(c->h_tab, tab + T_BSTART, 513 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    TRY(read_words(c, sm, 4));
+    uint32_t m = c->h_pin[0], sigma = c->h_pin[3];
+    TRY(post_classify(c, text, n, sigma));
+    c->lms_asc_ready = false;
+    *m_out = m;
+    return B200SA_OK;
+}
+
+// Text-order LMS positions + per-word LMS ranks (robust path, k_unrename): derived on demand.
+static int lms_ascending(b200sa_ctx *c, uint64_t n, uint32_t m) {
+    if (c->lms_asc_ready) return B200SA_OK;
+    uint64_t nw = (n + 31) / 32;
+    TRY(ensure(c, c->lmsrank, nw * 4));
+    TRY(ensure(c, c->lmspos, (size_t)m * 4));
+    TRY((dev_scan<OpSum>(c, InPopcWords{ptr<uint32_t>(c->lmsb)}, OutStoreExcl{ptr<uint32_t>(c->lmsrank)}, nw, nullptr)));
+    if (m > 0) LAUNCH(c, k_reverse_u32, cdiv(m, BLK), ptr<uint32_t>(c->lmsdesc), m, ptr<uint32_t>(c->lmspos));
+    CU_TRY(c, cudaGetLastError());
+    c->lms_asc_ready = true;
+    return B200SA_OK;
+}
+
+
 static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *m_out,
                         ShardEdge edge = ShardEdge{-1, -1, ST_L}) {
     uint64_t nw = (n + 31) / 32;
@@ -656,21 +766,13 @@ static int classify_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t
         CU_TRY(c, cudaMemcpyAsync(c->h_tab, tab + T_BSTART, 513 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     TRY(read_words(c, sm, 4));
     uint32_t m = c->h_pin[0], sigma = c->h_pin[3];
-    TRY(pack_text(c, text, n, sigma));
-    {   // grid of the persistent induce kernels: few buckets -> long lists, latency bound -> more blocks
-        // per SM; many buckets -> grid-sync bound -> one block per SM
-        int bps = sigma <= 16 ? 3 : (sigma <= 64 ? 2 : 1);
-        if (c->induce_bps_env) bps = c->induce_bps_env;
-        int occ_here = c->induce_occ[c->bits == 2 ? 0 : (c->bits == 4 ? 1 : 2)];
-        if (bps > occ_here) bps = occ_here;
-        if (bps < 1) bps = 1;
-        c->cur_induce_blocks = c->sm_count * bps;
-    }
+    TRY(post_classify(c, text, n, sigma));
     TRY(ensure(c, c->lmspos, (size_t)m * 4));
     if (m > 0) {
         LAUNCH(c, k_lms_positions, cdiv(nw, BLK), ptr<uint32_t>(c->lmsb), ptr<uint32_t>(c->lmsrank), nw, ptr<uint32_t>(c->lmspos));
         CU_TRY(c, cudaGetLastError());
     }
+    c->lms_asc_ready = true;
     *m_out = m;
     return B200SA_OK;
 }
@@ -711,7 +813,13 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     uint32_t n32 = (uint32_t)n;
     TRY(mark(c, "classify"));
     uint32_t m = 0;
-    TRY(classify_dev(c, text, n, &m));
+    if (getenv("B200SA_CLASSIFY_V1")) {          // three-kernel classifier (classify.cuh) + reversed position list
+        TRY(classify_dev(c, text, n, &m));
+        TRY(ensure(c, c->lmsdesc, (size_t)m * 4 + 16));
+        if (m > 0) LAUNCH(c, k_reverse_u32, cdiv(m, BLK), ptr<uint32_t>(c->lmspos), m, ptr<uint32_t>(c->lmsdesc));
+    } else {
+        TRY(classify_fused_dev(c, text, n, &m));
+    }
     c->stats.m = m; c->last_m = m;
     c->stats.induce_blocks = c->cur_induce_blocks;
     TRY(ensure(c, c->pred, n));
@@ -729,6 +837,7 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     c->stats.direct_sort = direct_done ? 1u : 0u;
     if (m > 0 && !direct_done) {
         c->stats.doubling_rounds = 0;
+        TRY(lms_ascending(c, n, m));              // text-order positions + per-word ranks for the robust path
         TRY(ensure(c, c->sorted, (size_t)m * 4));
         TRY(ensure(c, c->flag, m));
         TRY(ensure(c, c->reduced, (size_t)m * 4));
@@ -1006,15 +1115,19 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
     int occ = 0;
     {
         const int bb[3] = {2, 4, 8};
-        for (int k = 0; k < 3; k++) {
-            int ok = 1 << 30;
-            for (int sp = 0; sp < 2; sp++) {
-                int o = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, induce_fn(sp != 0, bb[k]), BLK, 0);
-                if (o < ok) ok = o;
+        for (int v = 1; v <= 3; v++)
+            for (int k = 0; k < 3; k++) {
+                int ok = 1 << 30;
+                for (int sp = 0; sp < 2; sp++) {
+                    int o = 0;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, induce_fn_v(sp != 0, bb[k], v), BLK, 0);
+                    if (o < ok) ok = o;
+                }
+                c->induce_occ_v[v][k] = ok > 4 ? 4 : ok;
             }
-            c->induce_occ[k] = ok > 4 ? 4 : ok;
-            if (c->induce_occ[k] > occ) occ = c->induce_occ[k];
+        for (int k = 0; k < 3; k++) {
+            c->induce_occ[k] = c->induce_occ_v[induce_variant(bb[k])][k];
+            for (int v = 1; v <= 3; v++) if (c->induce_occ_v[v][k] > occ) occ = c->induce_occ_v[v][k];
         }
     }
     if (occ < 1) { cudaFreeHost(c->h_pin); delete c; return B200SA_ERR_CUDA; }
@@ -1033,7 +1146,7 @@ void b200sa_ctx_destroy(b200sa_ctx *c) {
     DevBuf *bufs[] = {&c->text, &c->sa, &c->lcp, &c->pred, &c->stype, &c->lmsb, &c->lmsrank, &c->lmspos, &c->lmslist,
                       &c->lmspred, &c->sorted, &c->flag, &c->reduced, &c->sa_r, &c->blkstate, &c->carry, &c->tables,
                       &c->small, &c->scan_partial, &c->radix_cnt, &c->blkcnt, &c->k32b, &c->k64a, &c->k64b, &c->v0,
-                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr, &c->plcp_samp, &c->scan_state};
+                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr, &c->plcp_samp, &c->scan_state, &c->cls_state, &c->lmsdesc, &c->steplog};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -1276,6 +1389,28 @@ int b200sa_test_classify(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_
     return end_call(c);
 }
 
+int b200sa_test_classify_fused(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *stype_words, uint32_t *lms_words,
+                               uint32_t *hist768, uint32_t *lmspos_desc, uint64_t cap_lms, uint64_t *m_out) {
+    if (!c || !text || n < 1 || n > B200SA_MAX_N) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, nullptr);
+    TRY(ensure(c, c->text, n));
+    CU_TRY(c, cudaMemcpyAsync(c->text.p, text, n, cudaMemcpyHostToDevice, c->stream));
+    uint32_t m = 0;
+    TRY(classify_fused_dev(c, ptr<uint8_t>(c->text), n, &m));
+    uint64_t nw = (n + 31) / 32;
+    if (stype_words) CU_TRY(c, cudaMemcpyAsync(stype_words, c->stype.p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (lms_words) CU_TRY(c, cudaMemcpyAsync(lms_words, c->lmsb.p, nw * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (hist768) CU_TRY(c, cudaMemcpyAsync(hist768, ptr<uint32_t>(c->tables) + T_HIST, 768 * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (lmspos_desc && m > 0) {
+        uint64_t k = m < cap_lms ? m : cap_lms;
+        CU_TRY(c, cudaMemcpyAsync(lmspos_desc, c->lmsdesc.p, k * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (m_out) *m_out = m;
+    return end_call(c);
+}
+
 int b200sa_test_scan(b200sa_ctx *c, const uint32_t *in, uint64_t n, int op, uint32_t *out_excl, uint32_t *total) {
     if (!c || (n > 0 && (!in || !out_excl))) return B200SA_ERR_BAD_ARG;
     CU_TRY(c, cudaSetDevice(c->device));
@@ -1328,6 +1463,7 @@ int64_t b200sa_debug_fetch(b200sa_ctx *c, int which, void *out, uint64_t cap) {
         case 4: src = c->lmslist.p; count = c->last_m; break;
         case 5: src = c->small.p ? (const void *)(ptr<uint32_t>(c->small) + 32) : nullptr; count = 10; break;
         case 6: src = c->tables.p; count = T_HIST; break;
+        case 7: src = c->steplog.p; count = c->steplog.p ? 8192 : 0; break;     // u64 records viewed as u32 pairs
         default: return B200SA_ERR_BAD_ARG;
     }
     if (!src) return 0;

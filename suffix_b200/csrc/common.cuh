@@ -219,6 +219,53 @@ struct ScanState {
     uint32_t epoch;
 };
 
+// Warp-0 part of a tile: publishes the tile aggregate, walks back over the predecessors and
+// publishes the inclusive prefix.  All 32 lanes of ONE warp call it; returns the exclusive
+// prefix of the tile (in every lane).  `last` = this is the final tile (writes *d_total).
+template <class Op>
+__device__ __forceinline__ typename Op::T tile_lookback(const ScanState &S, uint32_t tile, typename Op::T block_total,
+                                                        bool last, typename Op::T *d_total) {
+    typedef typename Op::T T;
+    const uint32_t l = lane_id();
+    T prefix = Op::id();
+    if (tile > 0) {
+        if (l == 0) {
+            st_relaxed_u64(S.agg + tile, (unsigned long long)block_total);
+            __threadfence();
+            st_relaxed_u32(S.flag + tile, S.epoch + 1u);
+        }
+        int64_t t0 = (int64_t)tile - 1;
+        while (true) {
+            int64_t tt = t0 - (int64_t)l;            // lane 0: nearest predecessor
+            uint32_t st = 2u;                         // before tile 0: inclusive prefix = identity
+            T val = Op::id();
+            if (tt >= 0) {
+                uint32_t f;
+                do { f = ld_relaxed_u32(S.flag + tt) - S.epoch; } while (f != 1u && f != 2u);
+                __threadfence();
+                st = f;
+                val = (T)ld_relaxed_u64((f == 2u ? S.incl : S.agg) + tt);
+            }
+            uint32_t im = __ballot_sync(FULL, st == 2u);
+            uint32_t first = im ? (uint32_t)(__ffs(im) - 1) : 32u;
+            T contrib = (l <= first) ? val : Op::id();
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib = Op::op(contrib, __shfl_xor_sync(FULL, contrib, o));
+            prefix = Op::op(prefix, contrib);
+            if (im) break;
+            t0 -= 32;
+        }
+    }
+    if (l == 0) {
+        T total = Op::op(prefix, block_total);
+        st_relaxed_u64(S.incl + tile, (unsigned long long)total);
+        __threadfence();
+        st_relaxed_u32(S.flag + tile, S.epoch + 2u);
+        if (last && d_total) *d_total = total;
+    }
+    return prefix;
+}
+
 template <class Op, class InF, class OutF>
 __global__ void __launch_bounds__(BLK) k_scan_lb(InF in, OutF out, uint64_t n, uint32_t ntiles, ScanState S,
                                                  typename Op::T *d_total) {
@@ -255,42 +302,7 @@ __global__ void __launch_bounds__(BLK) k_scan_lb(InF in, OutF out, uint64_t n, u
         const T block_total = shfl_t(inc, NWARP - 1);
         T prevw = __shfl_up_sync(FULL, inc, 1);
         T wexc = (l == 0) ? Op::id() : prevw;          // exclusive prefix of warp l inside the block
-        T prefix = Op::id();
-        if (tile > 0) {
-            if (l == 0) {
-                st_relaxed_u64(S.agg + tile, (unsigned long long)block_total);
-                __threadfence();
-                st_relaxed_u32(S.flag + tile, S.epoch + 1u);
-            }
-            int64_t t0 = (int64_t)tile - 1;
-            while (true) {
-                int64_t tt = t0 - (int64_t)l;            // lane 0: nearest predecessor
-                uint32_t st = 2u;                         // before tile 0: inclusive prefix = identity
-                T val = Op::id();
-                if (tt >= 0) {
-                    uint32_t f;
-                    do { f = ld_relaxed_u32(S.flag + tt) - S.epoch; } while (f != 1u && f != 2u);
-                    __threadfence();
-                    st = f;
-                    val = (T)ld_relaxed_u64((f == 2u ? S.incl : S.agg) + tt);
-                }
-                uint32_t im = __ballot_sync(FULL, st == 2u);
-                uint32_t first = im ? (uint32_t)(__ffs(im) - 1) : 32u;
-                T contrib = (l <= first) ? val : Op::id();
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) contrib = Op::op(contrib, __shfl_xor_sync(FULL, contrib, o));
-                prefix = Op::op(prefix, contrib);
-                if (im) break;
-                t0 -= 32;
-            }
-        }
-        if (l == 0) {
-            T total = Op::op(prefix, block_total);
-            st_relaxed_u64(S.incl + tile, (unsigned long long)total);
-            __threadfence();
-            st_relaxed_u32(S.flag + tile, S.epoch + 2u);
-            if (tile + 1 == ntiles && d_total) *d_total = total;
-        }
+        T prefix = tile_lookback<Op>(S, tile, block_total, tile + 1 == ntiles, d_total);
         if (l < (uint32_t)NWARP) s_w[l] = Op::op(prefix, wexc);
     }
     __syncthreads();

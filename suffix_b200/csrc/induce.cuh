@@ -45,6 +45,7 @@ struct InduceArgs {
     uint32_t *run_scratch;   // [TILE] run-skipping: terminal entries in scan order
     uint32_t *run_alive;     // [TILE] run-skipping: alive entries of the epoch being emitted grid-wide
     uint32_t *cmd;           // [8]    block 0 -> grid: {cmd, a, t_prev, rounds, base pos, bucket}
+    unsigned long long *steplog;   // diagnostics (B200SA_STEPLOG): [0] = count, then (globaltimer ns, list length) pairs
 };
 enum { CMD_NONE = 0, CMD_EMIT = 1, CMD_DONE = 2 };
 constexpr uint64_t EMIT_GRID_MIN = 32768;   // epochs with at least this many entries are emitted by the whole grid

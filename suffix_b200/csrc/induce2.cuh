@@ -24,8 +24,7 @@
 // chain round (100 MB DNA: 4 big steps per pass instead of 23 big + 19 small).
 // Lists of at most TILE entries and very long runs take the small-episode path of
 // induce.cuh (block 0, run skipping) unchanged.
-// Executable model: tests/model_pipeline.py::induce_multiround (validated against the
-// oracle in tests/test_model.py).
+// Executable model: tests/model_pipeline.py::induce_multiround (tests/test_model.py).
 #pragma once
 #include "induce.cuh"
 

@@ -79,32 +79,31 @@ __device__ __forceinline__ uint32_t lms_window(const LmsWin &W, uint32_t p) {
     }
 }
 
-// first-pass functors of the one-sweep sort: item i = LMS position lmspos[m-1-i]
+// first-pass functors of the one-sweep sort: item i = i-th LMS position from the END of the
+// text (the fused classifier emits them in that order)
 template <int BITS>
 struct LmsKeyDesc {
-    LmsWin W; const uint32_t *lmspos; uint32_t m;
-    __device__ __forceinline__ uint32_t operator()(uint64_t i) const {
-        return lms_window<BITS>(W, __ldg(lmspos + (m - 1u - (uint32_t)i)));
-    }
+    LmsWin W; const uint32_t *lmsdesc;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return lms_window<BITS>(W, __ldg(lmsdesc + i)); }
 };
 struct LmsValDesc {
-    const uint32_t *lmspos; uint32_t m;
-    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return __ldg(lmspos + (m - 1u - (uint32_t)i)); }
+    const uint32_t *lmsdesc;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return __ldg(lmsdesc + i); }
 };
 
 // ---- round 1: groups of equal window keys in the sorted list (slot = index).
 // Only LMS positions inside the last `span` characters can be truncated (at most span/2
-// of them, the last entries of lmspos).  One small kernel finds their slots -- they
+// of them, the first entries of the descending list).  One small kernel finds their slots -- they
 // stand at the very start of their run of equal keys, in descending position -- and
 // sets "forced head" bits for the slot and its successor, so that the scan over all m
 // elements reads the keys only.
 template <int BITS>
-__global__ void __launch_bounds__(BLK) k_lms_mark_trunc(LmsWin W, const uint32_t *__restrict__ lmspos, uint32_t m,
+__global__ void __launch_bounds__(BLK) k_lms_mark_trunc(LmsWin W, const uint32_t *__restrict__ lmsdesc, uint32_t m,
                                                         const uint32_t *__restrict__ K, const uint32_t *__restrict__ P,
                                                         uint32_t span, uint32_t *forced) {
     uint32_t t = threadIdx.x;
     if (t >= m || t >= span) return;
-    uint32_t p = lmspos[m - 1u - t];
+    uint32_t p = lmsdesc[t];
     if ((uint64_t)p + span <= W.n) return;                // not truncated
     uint32_t key = lms_window<BITS>(W, p);
     uint32_t lo = 0, hi = m;
@@ -122,13 +121,18 @@ __global__ void __launch_bounds__(BLK) k_lms_mark_trunc(LmsWin W, const uint32_t
 }
 struct InLmsActive1 {
     const uint32_t *K, *forced; uint32_t m;
+    // branch-free: all five loads of an element are independent (a short-circuit chain would
+    // serialise them behind branches; measured 3x slower)
     __device__ __forceinline__ bool head(uint32_t i) const {
-        return i == 0 || K[i] != K[i - 1] || ((forced[i >> 5] >> (i & 31)) & 1u);
+        uint32_t a = K[i], b = K[i > 0 ? i - 1 : 0], f = forced[i >> 5];
+        return (i == 0) | (a != b) | ((f >> (i & 31)) & 1u);
     }
-    __device__ uint32_t operator()(uint64_t ii) const {
-        uint32_t i = (uint32_t)ii;
-        bool hd = head(i), tl = (i + 1 == m) || head(i + 1);
-        return (hd && tl) ? 0u : 1u;
+    __device__ __forceinline__ uint32_t operator()(uint64_t ii) const {
+        uint32_t i = (uint32_t)ii, j = i + 1 < m ? i + 1 : i;
+        uint32_t a = K[i], b = K[i > 0 ? i - 1 : 0], c = K[j], f = forced[i >> 5], f2 = forced[j >> 5];
+        bool hd = (i == 0) | (a != b) | ((f >> (i & 31)) & 1u);
+        bool tl = (i + 1 == m) | (c != a) | ((f2 >> (j & 31)) & 1u);
+        return (hd & tl) ? 0u : 1u;
     }
 };
 // compaction of the tied elements; ahead[k] = slot if the element starts its group, else 0

@@ -70,7 +70,7 @@ def test_sort_pairs64(ctx, n, bits):
     assert np.array_equal(v, vals[order])
 
 
-def _classify(ctx, t):
+def _classify(ctx, t, fused=False):
     n = len(t)
     nw = (n + 31) // 32
     st = np.zeros(nw, dtype=np.uint32)
@@ -78,10 +78,12 @@ def _classify(ctx, t):
     hist = np.zeros(768, dtype=np.uint32)
     pos = np.zeros(max(1, n // 2 + 1), dtype=np.uint32)
     m = ctypes.c_uint64(0)
-    _check(ctx, _lib.lib().b200sa_test_classify(ctx._h, t.ctypes.data, n, st.ctypes.data, lm.ctypes.data,
-                                                hist.ctypes.data, pos.ctypes.data, len(pos), ctypes.byref(m)))
+    fn = _lib.lib().b200sa_test_classify_fused if fused else _lib.lib().b200sa_test_classify
+    _check(ctx, fn(ctx._h, t.ctypes.data, n, st.ctypes.data, lm.ctypes.data,
+                   hist.ctypes.data, pos.ctypes.data, len(pos), ctypes.byref(m)))
     bits = lambda w: np.unpackbits(w.view(np.uint8), bitorder="little")[:n]
-    return bits(st), bits(lm), hist, pos[: m.value]
+    p = pos[: m.value]
+    return bits(st), bits(lm), hist, (p[::-1] if fused else p)      # the fused kernel lists positions from the end
 
 
 def _classify_cases():
@@ -91,15 +93,21 @@ def _classify_cases():
     out += [("dna_1m", gen.dna(1_000_003)), ("bytes_300k", gen.rand_bytes(300_001)),
             ("a^100k", np.full(100_000, 97, dtype=np.uint8)),
             ("a^8192 b", np.concatenate([np.full(8192 * 3, 97, dtype=np.uint8), np.array([98], dtype=np.uint8)])),
-            ("b a^8192..", np.concatenate([np.array([98], dtype=np.uint8), np.full(8192 * 3 + 5, 97, dtype=np.uint8)]))]
+            ("b a^8192..", np.concatenate([np.array([98], dtype=np.uint8), np.full(8192 * 3 + 5, 97, dtype=np.uint8)])),
+            ("a^300k b a^300k c", np.concatenate([np.full(300_000, 97, dtype=np.uint8), np.array([98], dtype=np.uint8),
+                                                  np.full(300_000, 97, dtype=np.uint8), np.array([99], dtype=np.uint8)])),
+            ("z^70k a z^70k", np.concatenate([np.full(70_000, 122, dtype=np.uint8), np.array([97], dtype=np.uint8),
+                                              np.full(70_000, 122, dtype=np.uint8)])),
+            ("english_200k", gen.english(200_003))]
     return out
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["three_kernel", "fused"])
 @pytest.mark.parametrize("name,t", _classify_cases(), ids=lambda x: x if isinstance(x, str) else "")
-def test_classify(ctx, name, t):
+def test_classify(ctx, name, t, fused):
     t = np.ascontiguousarray(t)
     ty = oracle.types(t)                      # 0 S, 1 L, 2 Valley (reference semantics)
-    sbit, lbit, hist, pos = _classify(ctx, t)
+    sbit, lbit, hist, pos = _classify(ctx, t, fused)
     assert np.array_equal(sbit, (ty != 1).astype(np.uint8))
     assert np.array_equal(lbit, (ty == 2).astype(np.uint8))
     assert np.array_equal(pos, np.flatnonzero(ty == 2).astype(np.uint32))

@@ -7,5 +7,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$RE
     -o /tmp/prof/$NAME -f python tools/one_build.py $N $KIND > gpurun_out/ncu_${NAME}_${TAG}.log 2>&1
 echo "ncu $NAME exit $?"
 python tools/ncu_summarize.py full /tmp/prof/$NAME.ncu-rep gpurun_out/ncu_${NAME}_${TAG}.json
-ncu -i /tmp/prof/$NAME.ncu-rep --page source --csv > gpurun_out/src_${NAME}_${TAG}.csv 2>/dev/null
+(ncu -i /tmp/prof/$NAME.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/src_${NAME}_${TAG}.csv 2>/dev/null || ncu -i /tmp/prof/$NAME.ncu-rep --page source --csv > gpurun_out/src_${NAME}_${TAG}.csv 2>/dev/null)
+ncu -i /tmp/prof/$NAME.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_stalls.py > gpurun_out/stalls_${NAME}_${TAG}.txt
 ls -la /tmp/prof/$NAME.ncu-rep gpurun_out/src_${NAME}_${TAG}.csv
