@@ -202,6 +202,60 @@ def _config(n, world):
             "timing": "GPU arm: CUDA events on the launching stream, max over ranks; reference arm: host clock"}
 
 
+def _sharded_record(args, ctx, dist, rank, world, dev):
+    """BASELINE configs[4]: world x shard_bytes of G_dna as ONE text, one contiguous shard per GPU;
+    type classification + LMS-suffix sort (b200sa_shard_lms_sort: NCCL all-gathers of the summaries,
+    one all-to-all of (key, position) pairs over NVLink).  Device time, max over ranks."""
+    import torch
+    from suffix_b200 import sharded
+    nb = args.shard_bytes
+    text = gen.dna(nb, seed=gen.SEED_DNA + rank)           # SURVEY 8d config 5: seed + shard id
+    shard = torch.from_numpy(text).to(dev)
+    sharded.ensure_comm(ctx, dist)
+    cap = nb // 2 + 4096
+    gpos = torch.empty(cap, dtype=torch.int64, device=dev)
+    names = torch.empty(cap, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    st = None
+    times = []
+    for it in range(3):                                    # 1 warm-up + 2 timed
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = ctx.shard_lms_sort(shard.data_ptr(), nb, gpos.data_ptr(), names.data_ptr(), cap, stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    phases = dict(ctx.phase_times())
+    k = int(st["recv_count"])
+    # local sanity: positions of this slice that lie in this rank's own shard are ordered by their windows
+    g = gpos[:k]
+    mine = g[(g >= st["lo"]) & (g < st["lo"] + nb - 64)][:200000].cpu().numpy() - st["lo"]
+    tb = text.tobytes()
+    kc = int(st["kc"])
+    ok = all(tb[int(a):int(a) + kc] <= tb[int(b):int(b) + kc] for a, b in zip(mine[:-1], mine[1:]))
+    nm = names[:k]
+    ok = ok and bool(((nm[1:] - nm[:-1]) >= 0).all().item()) if k > 1 else ok
+    t = torch.tensor([min(times[1:]), st["bytes_sent"], float(k), 1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    ms = float(tmax[0].item())
+    total = nb * world
+    del gpos, names, shard
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[4]: %d x %d B of G_dna as ONE text, type-classify + LMS-suffix sort sharded over "
+                        "%d GPUs (b200sa_shard_lms_sort, NCCL inside the library)" % (world, nb, world),
+            "n_bytes_total": total, "ms_per_step": round(ms, 3),
+            "GBps_aggregate": round(total / 1e9 / (ms / 1e3), 2), "GBps_per_gpu": round(nb / 1e9 / (ms / 1e3), 2),
+            "m_total": int(st["m_total"]), "slice_sum": int(tsum[2].item()), "window_chars": kc,
+            "ties_total": int(st["ties_total"]), "nvlink_bytes_per_step": int(tsum[1].item()),
+            "checks_ok": bool(tmin[3].item() == 1.0) and int(tsum[2].item()) == int(st["m_total"]),
+            "phase_ms_rank0": {k2: round(v, 3) for k2, v in phases.items()},
+            "timing": "CUDA events on the launching stream around the collective call, max over ranks, best of 2 after 1 warm-up"}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -286,6 +340,12 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_result_check = int(h_lcp[0].item()) + int(h_sa[0].item() >= 0)   # touch the result
 
+    # ---------------- N > 1: ONE text sharded over the GPUs (BASELINE config 5):
+    # classification + LMS-suffix sort of N x shard_bytes of G_dna with NCCL inside the library
+    sharded_rec = None
+    if world > 1 and not args.no_sharded:
+        sharded_rec = _sharded_record(args, ctx, dist, rank, world, dev)
+
     # ---------------- max over ranks
     if world > 1:
         tt = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
@@ -310,27 +370,33 @@ def run_gpu(args):
         ind_ms = statistics.mean(ind.values()) if ind else None
         alg = (bytes_L + bytes_S) / 2.0
         achieved = alg / 1e9 / (ind_ms / 1e3) if ind_ms else None
-        traffic = None
+        traffic, traffic_src = None, None
         ncu_p = os.path.join(ROOT, "profiles", "ncu_summary.json")
         if os.path.exists(ncu_p):
             try:
-                traffic = json.load(open(ncu_p)).get("k_induce", {}).get("dram_bytes_per_launch")
+                rec = json.load(open(ncu_p)).get("k_induce", {})
+                traffic, traffic_src = rec.get("dram_bytes_per_launch"), rec.get("source")
             except Exception:
                 traffic = None
         phase_ms = {k: round(statistics.mean(v), 3) for k, v in phase_acc.items()}
         dom_share = (sum(ind.values()) / (ms_dev / steps)) if ind else None
-        # per-phase achieved GB/s against the same peak (SURVEY.md Appendix D bytes, level 0, w = 1)
-        appd = {"classify": 2 * n, "lms_group": 9 * m, "induce1_L": bytes_L, "induce1_S": bytes_S,
+        # per-phase achieved GB/s against the same peak (SURVEY.md Appendix D bytes, level 0, w = 1; the
+        # LMS sort has no App. D row: 4 one-sweep passes x (8 B in + 8 B out) x m + the digit-histogram read)
+        appd = {"classify": 2 * n, "lms_sort": 4 * 16 * m + 4 * m, "lms_groups": 8 * m, "lms_group": 9 * m,
+                "induce1_L": bytes_L, "induce1_S": bytes_S,
                 "induce2_L": bytes_L, "induce2_S": bytes_S, "compact_lms": 4 * n + n / 8 + 4 * m,
-                "name": 8 * n + 4 * m, "unrename": 16 * m, "lcp_phi": 8 * n, "lcp_plcp": 12 * n, "lcp_gather": 12 * n}
+                "name": 8 * n + 4 * m, "unrename": 16 * m, "lcp_direct": 8 * n, "lcp_phi": 8 * n, "lcp_plcp": 12 * n,
+                "lcp_gather": 12 * n}
         phases_roof = {}
         for k, b in appd.items():
             if k in phase_ms and phase_ms[k] > 0:
                 g = b / 1e9 / (phase_ms[k] / 1e3)
                 phases_roof[k] = {"GBps": round(g, 1), "frac": round(g / peak, 4)}
-        roof = {"bound": "hbm", "kernel": "k_induce<L|S> (mean of the 4 persistent launches per build)",
+        n_ind = len(ind)
+        roof = {"bound": "hbm", "kernel": "induce pass kernels (k_induce3<L|S> on 2-bit text; mean of the %d persistent launches per build)" % n_ind,
                 "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg),
                 "kernel_ms_per_launch": round(ind_ms, 4) if ind_ms else None,
                 "share_of_step": round(dom_share, 3) if dom_share else None,
@@ -363,6 +429,8 @@ def run_gpu(args):
             "levels": {"n": n, "m": stats["m"], "names": stats["names"], "doubling_rounds": stats["doubling_rounds"]},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
+        if sharded_rec is not None:
+            out["sharded"] = sharded_rec
         _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -395,6 +463,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_TEXT, help="text bytes per GPU (default: the 100 MB config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded config-5 record")
+    ap.add_argument("--shard-bytes", type=int, default=1_000_000_000, help="N > 1: bytes per GPU of the sharded text")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -41,7 +41,8 @@ enum {
     B200SA_ERR_NO_DEVICE = -3,
     B200SA_ERR_OOM       = -4,
     B200SA_ERR_CUDA      = -5,
-    B200SA_ERR_INTERNAL  = -6   /* device-side invariant violated                 */
+    B200SA_ERR_INTERNAL  = -6,  /* device-side invariant violated                 */
+    B200SA_ERR_COMM      = -7   /* NCCL missing or a collective failed            */
 };
 
 /* Context: binds a CUDA device, one stream, the device workspace. */
@@ -116,6 +117,50 @@ int b200sa_shard_summary(b200sa_ctx *ctx, const uint8_t *d_shard, uint64_t len, 
 int b200sa_shard_classify(b200sa_ctx *ctx, const uint8_t *d_shard, uint64_t len, int prev_char, int next_char,
                           int tail_carry, uint32_t *d_stype_words, uint32_t *d_lms_words,
                           uint32_t *d_lmspos, uint64_t cap_lms, uint64_t *hist768, uint64_t *m_out, void *stream);
+
+/* ---- multi-GPU: communicator + sharded LMS-suffix sort ----
+ * One process (or thread) and one context per GPU.  NCCL is resolved at run time
+ * (the copy already loaded in the process, else libnccl.so.2); the single-GPU entry
+ * points never touch it.  Either let the library create the communicator --
+ * rank 0 calls b200sa_comm_unique_id, the application hands the 128 bytes to every
+ * rank (MPI, torch.distributed, a file), every rank calls b200sa_comm_init -- or
+ * attach an ncclComm_t the application already owns (same NCCL instance).
+ *
+ * b200sa_shard_lms_sort (collective): rank r passes its contiguous shard of the
+ * text (rank order = text order; 16-byte aligned device pointer).  The shards are
+ * classified (types, LMS positions; halo chars and carries exchanged), then the
+ * LMS suffixes of the WHOLE text are ordered by their first kc characters (64-bit
+ * window keys, zero-padded past the end of the text) with one sample-sort
+ * exchange: rank r ends up with the r-th slice of the global order.
+ *   d_sorted_gpos[i]  global text position of the i-th LMS suffix of this slice
+ *   d_names[i]        dense global rank of its window (equal windows share a name)
+ *   out->ties_total   members of groups of equal windows over all ranks; 0 means
+ *                     the slices ARE the LMS suffixes in suffix order
+ * Replaces, for a sharded text, src/table.rs:411-416 (LMS placement), :421-448
+ * (first induce) and :450-482 (compaction + naming). */
+typedef struct {
+    uint64_t n_total;        /* bytes of the whole text                                 */
+    uint64_t m_total;        /* LMS suffixes of the whole text                          */
+    uint64_t m_local;        /* LMS suffixes of this shard                              */
+    uint64_t lo;             /* global offset of this shard                             */
+    uint64_t recv_count;     /* entries of this rank's slice of the global order        */
+    uint64_t distinct_local; /* distinct windows in the slice                           */
+    uint64_t name_offset;    /* distinct windows on lower ranks                         */
+    uint64_t ties_total;     /* members of non-singleton window groups, all ranks       */
+    double   bytes_sent;     /* payload this rank sent to OTHER ranks (NVLink)          */
+    double   bytes_recv;
+    uint32_t kc;             /* characters per window                                   */
+    uint32_t nranks, rank;
+    uint32_t reserved;
+} b200sa_shard_stats;
+
+int b200sa_comm_unique_id(uint8_t *id128_out);
+int b200sa_comm_init(b200sa_ctx *ctx, int nranks, int rank, const uint8_t *id128);
+int b200sa_comm_attach(b200sa_ctx *ctx, void *nccl_comm);
+int b200sa_comm_destroy(b200sa_ctx *ctx);
+int b200sa_shard_lms_sort(b200sa_ctx *ctx, const uint8_t *d_shard, uint64_t len,
+                          unsigned long long *d_sorted_gpos, uint32_t *d_names, uint64_t cap,
+                          b200sa_shard_stats *out, void *stream);
 
 /* ---- introspection (bench / tests) ---- */
 

@@ -22,6 +22,14 @@ class Stats(ctypes.Structure):
                 ("workspace_bytes", ctypes.c_uint64), ("direct_sort", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
+class ShardStats(ctypes.Structure):
+    _fields_ = [("n_total", ctypes.c_uint64), ("m_total", ctypes.c_uint64), ("m_local", ctypes.c_uint64),
+                ("lo", ctypes.c_uint64), ("recv_count", ctypes.c_uint64), ("distinct_local", ctypes.c_uint64),
+                ("name_offset", ctypes.c_uint64), ("ties_total", ctypes.c_uint64),
+                ("bytes_sent", ctypes.c_double), ("bytes_recv", ctypes.c_double),
+                ("kc", ctypes.c_uint32), ("nranks", ctypes.c_uint32), ("rank", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
 _lib = None
 
 
@@ -47,6 +55,11 @@ def lib():
         "b200sa_positions_dev": ([vp, vp, u64, vp, vp, vp, u32, vp, vp, vp], ci),
         "b200sa_shard_summary": ([vp, vp, u64, ci, ctypes.POINTER(ci), vp], ci),
         "b200sa_shard_classify": ([vp, vp, u64, ci, ci, ci, vp, vp, vp, u64, vp, ctypes.POINTER(u64), vp], ci),
+        "b200sa_comm_unique_id": ([vp], ci),
+        "b200sa_comm_init": ([vp, ci, ci, vp], ci),
+        "b200sa_comm_attach": ([vp, vp], ci),
+        "b200sa_comm_destroy": ([vp], ci),
+        "b200sa_shard_lms_sort": ([vp, vp, u64, vp, vp, u64, ctypes.POINTER(ShardStats), vp], ci),
         "b200sa_last_stats": ([vp, ctypes.POINTER(Stats)], ci),
         "b200sa_set_timing": ([vp, ci], ci),
         "b200sa_last_phase_times": ([vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ci], ci),
@@ -145,6 +158,28 @@ class Context:
                                                 d_stype, d_lms, d_lmspos, cap_lms, hist.ctypes.data,
                                                 ctypes.byref(m), stream))
         return hist, int(m.value)
+
+    # communicator of the sharded entry points: NCCL inside the library (resolved at run time)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (ctypes.c_uint8 * 128)()
+        rc = lib().b200sa_comm_unique_id(buf)
+        if rc != 0:
+            raise B200SAError(rc, "b200sa_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(lib().b200sa_comm_init(self._h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        self._check(lib().b200sa_comm_destroy(self._h))
+
+    def shard_lms_sort(self, d_shard: int, length: int, d_gpos: int, d_names: int, cap: int, stream: int = 0) -> dict:
+        """Collective (b200sa_shard_lms_sort): this rank's slice of the global LMS-suffix order."""
+        st = ShardStats()
+        self._check(lib().b200sa_shard_lms_sort(self._h, d_shard, length, d_gpos, d_names, cap, ctypes.byref(st), stream))
+        return {f: getattr(st, f) for f, _ in ShardStats._fields_}
 
     # ---- introspection
     def set_timing(self, on: bool):

@@ -25,6 +25,8 @@
 #include "induce4.cuh"
 #include "pipeline_kernels.cuh"
 #include "lms_sort.cuh"
+#include "shard.cuh"
+#include "nccl_dyn.h"
 
 using namespace b200sa;
 
@@ -67,8 +69,13 @@ struct b200sa_ctx {
     DevBuf blkstate, carry, tables, small, scan_partial, radix_cnt, blkcnt;
     DevBuf os_hist, os_status, phik, phiv, runscr, plcp_samp;
     DevBuf k32b, k64a, k64b, v0, v1, p0, p1, g0, g1, rank, isa, qbuf;
-    DevBuf packed, scan_state, cls_state, lmsdesc, steplog;
+    DevBuf packed, scan_state, cls_state, lmsdesc, steplog, hist_copies;
     uint32_t cls_calls = 0;
+    // multi-GPU: communicator owned or attached, NCCL resolved at run time
+    ncclComm_t comm = nullptr;
+    bool comm_owned = false;
+    int nranks = 1, comm_rank = 0;
+    DevBuf sh_a, sh_b, sh_c, sh_d, sh_e, sh_f, sh_small;
     bool lms_asc_ready = false;       // c->lmspos / c->lmsrank (text order) valid for the current text
     uint32_t scan_epoch = 0, scan_tiles_cap = 0;
     bool l2_persist = false;          // access policy window for the packed text (B200SA_L2PERSIST)
@@ -470,7 +477,7 @@ static int pack_text(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t si
     if (sigma <= 4) c->bits = 2; else if (sigma <= 16) c->bits = 4; else return B200SA_OK;
     uint32_t cpw = 32 / c->bits;
     uint64_t words = (n + cpw - 1) / cpw;
-    TRY(ensure(c, c->packed, words * 4 + 8));   // + one padding word for text_bits()
+    TRY(ensure(c, c->packed, words * 4 + 32));  // + padding for text_bits() / text_bits_wide()
     if (c->bits == 2) LAUNCH(c, (k_pack<2>), cdiv(words, BLK), text, n, tab + T_CODE, ptr<uint32_t>(c->packed));
     else LAUNCH(c, (k_pack<4>), cdiv(words, BLK), text, n, tab + T_CODE, ptr<uint32_t>(c->packed));
     CU_TRY(c, cudaGetLastError());
@@ -698,7 +705,8 @@ static int scan_state_for(b200sa_ctx *c, uint32_t nb, ScanState *S) {
 
 // K1 fused (classify2.cuh): one pass -> type / LMS bitmaps, (byte, type) histogram, bucket
 // tables, LMS positions in descending text order (c->lmsdesc), packed text.
-static int classify_fused_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *m_out) {
+static int classify_fused_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_t *m_out,
+                              ShardEdge edge = ShardEdge{-1, -1, ST_L}, bool pack = true) {
     uint64_t nw = (n + 31) / 32;
     uint32_t nbc = cdiv(nw, CLS_WORDS);
     TRY(ensure(c, c->stype, nw * 4));
@@ -711,13 +719,15 @@ static int classify_fused_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, ui
         CU_TRY(c, cudaMemsetAsync(c->cls_state.p, 0, c->cls_state.cap, c->stream));
     }
     uint32_t *tab = ptr<uint32_t>(c->tables), *hist = tab + T_HIST, *sm = ptr<uint32_t>(c->small);
-    CU_TRY(c, cudaMemsetAsync(hist, 0, 768 * 4, c->stream));
+    TRY(ensure(c, c->hist_copies, (size_t)HIST_COPIES * 768 * 4));
+    CU_TRY(c, cudaMemsetAsync(c->hist_copies.p, 0, (size_t)HIST_COPIES * 768 * 4, c->stream));
     CU_TRY(c, cudaMemsetAsync(sm, 0, 4096, c->stream));
     ScanState S;
     TRY(scan_state_for(c, nbc, &S));
     Cls2State CS{ptr<uint32_t>(c->cls_state), (++c->cls_calls) * 8u};
-    LAUNCH(c, k_classify_fused, nbc, text, n, nbc, S, CS, ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb), hist,
-           ptr<uint32_t>(c->lmsdesc), sm, ShardEdge{-1, -1, ST_L});
+    LAUNCH(c, k_classify_fused, nbc, text, n, nbc, S, CS, ptr<uint32_t>(c->stype), ptr<uint32_t>(c->lmsb),
+           ptr<uint32_t>(c->hist_copies), ptr<uint32_t>(c->lmsdesc), sm, edge);
+    LAUNCH(c, k_hist_fold, 1u, ptr<uint32_t>(c->hist_copies), hist);
     LAUNCH(c, k_bucket_tables, 1, hist, tab + T_BSTART, tab + T_LCNT, tab + T_SCNT, tab + T_LMSOFF, tab + T_CODE,
            tab + T_ALPHA, sm + 3);
     CU_TRY(c, cudaGetLastError());
@@ -725,7 +735,7 @@ static int classify_fused_dev(b200sa_ctx *c, const uint8_t *text, uint64_t n, ui
         CU_TRY(c, cudaMemcpyAsync(c->h_tab, tab + T_BSTART, 513 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     TRY(read_words(c, sm, 4));
     uint32_t m = c->h_pin[0], sigma = c->h_pin[3];
-    TRY(post_classify(c, text, n, sigma));
+    if (pack) TRY(post_classify(c, text, n, sigma));
     c->lms_asc_ready = false;
     *m_out = m;
     return B200SA_OK;
@@ -1149,10 +1159,11 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
 void b200sa_ctx_destroy(b200sa_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->comm && c->comm_owned && nccl_api().ok) nccl_api().CommDestroy(c->comm);
     DevBuf *bufs[] = {&c->text, &c->sa, &c->lcp, &c->pred, &c->stype, &c->lmsb, &c->lmsrank, &c->lmspos, &c->lmslist,
                       &c->lmspred, &c->sorted, &c->flag, &c->reduced, &c->sa_r, &c->blkstate, &c->carry, &c->tables,
                       &c->small, &c->scan_partial, &c->radix_cnt, &c->blkcnt, &c->k32b, &c->k64a, &c->k64b, &c->v0,
-                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr, &c->plcp_samp, &c->scan_state, &c->cls_state, &c->lmsdesc, &c->steplog};
+                      &c->v1, &c->p0, &c->p1, &c->g0, &c->g1, &c->rank, &c->isa, &c->qbuf, &c->os_hist, &c->os_status, &c->packed, &c->phik, &c->phiv, &c->runscr, &c->plcp_samp, &c->scan_state, &c->cls_state, &c->lmsdesc, &c->steplog, &c->hist_copies, &c->sh_a, &c->sh_b, &c->sh_c, &c->sh_d, &c->sh_e, &c->sh_f, &c->sh_small};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -1369,6 +1380,296 @@ int b200sa_shard_classify(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, i
         CU_TRY(c, cudaStreamSynchronize(c->stream));
     }
     if (m_out) *m_out = m;
+    return end_call(c);
+}
+
+// ------------------------------------------------------------ multi-GPU: communicator + sharded LMS sort
+#define NCCL_TRY(ctx, expr)                                                                  \
+    do {                                                                                     \
+        ncclResult_t r__ = (expr);                                                           \
+        if (r__ != ncclSuccess) {                                                            \
+            char buf__[400];                                                                 \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,      \
+                     nccl_api().GetErrorString ? nccl_api().GetErrorString(r__) : "nccl error"); \
+            (ctx)->last_error = buf__;                                                       \
+            return B200SA_ERR_COMM;                                                          \
+        }                                                                                    \
+    } while (0)
+
+int b200sa_comm_unique_id(uint8_t *id_out) {
+    if (!id_out) return B200SA_ERR_BAD_ARG;
+    NcclApi &N = nccl_api();
+    if (!N.ok) return B200SA_ERR_COMM;
+    ncclUniqueId id;
+    if (N.GetUniqueId(&id) != ncclSuccess) return B200SA_ERR_COMM;
+    memcpy(id_out, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return B200SA_OK;
+}
+
+int b200sa_comm_init(b200sa_ctx *c, int nranks, int rank, const uint8_t *id128) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks || nranks > 16) return B200SA_ERR_BAD_ARG;
+    NcclApi &N = nccl_api();
+    if (!N.ok) { c->last_error = N.err; return B200SA_ERR_COMM; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (c->comm && c->comm_owned) N.CommDestroy(c->comm);
+    c->comm = nullptr;
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    NCCL_TRY(c, N.CommInitRank(&c->comm, nranks, id, rank));
+    c->comm_owned = true; c->nranks = nranks; c->comm_rank = rank;
+    return B200SA_OK;
+}
+
+int b200sa_comm_attach(b200sa_ctx *c, void *nccl_comm) {
+    if (!c || !nccl_comm) return B200SA_ERR_BAD_ARG;
+    NcclApi &N = nccl_api();
+    if (!N.ok) { c->last_error = N.err; return B200SA_ERR_COMM; }
+    if (c->comm && c->comm_owned) N.CommDestroy(c->comm);
+    c->comm = (ncclComm_t)nccl_comm;
+    c->comm_owned = false;
+    NCCL_TRY(c, N.CommCount(c->comm, &c->nranks));
+    NCCL_TRY(c, N.CommUserRank(c->comm, &c->comm_rank));
+    if (c->nranks > 16) return B200SA_ERR_BAD_ARG;
+    return B200SA_OK;
+}
+
+int b200sa_comm_destroy(b200sa_ctx *c) {
+    if (!c) return B200SA_ERR_BAD_ARG;
+    if (c->comm && c->comm_owned && nccl_api().ok) nccl_api().CommDestroy(c->comm);
+    c->comm = nullptr; c->comm_owned = false; c->nranks = 1; c->comm_rank = 0;
+    return B200SA_OK;
+}
+
+// Collective over the context's communicator (a context without one is a world of 1).
+int b200sa_shard_lms_sort(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, unsigned long long *d_sorted_gpos,
+                          uint32_t *d_names, uint64_t cap, b200sa_shard_stats *out, void *stream) {
+    if (!c || !d_shard || len < 1 || len > B200SA_MAX_N || !out) return B200SA_ERR_BAD_ARG;
+    if (((uintptr_t)d_shard & 15) != 0) { c->last_error = "shard pointer must be 16-byte aligned"; return B200SA_ERR_BAD_ARG; }
+    NcclApi &N = nccl_api();
+    const int W = c->comm ? c->nranks : 1, R = c->comm ? c->comm_rank : 0;
+    if (W > 1 && !N.ok) { c->last_error = N.err; return B200SA_ERR_COMM; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    memset(out, 0, sizeof *out);
+    constexpr int HEAD = 64;                                   // bytes of every shard's head that travel (halo source)
+    // ---- small exchange area: per rank {len, first byte, last byte, state, m, distinct} + head bytes
+    const size_t REC = 8;                                      // u64 words per rank record
+    TRY(ensure(c, c->sh_small, (size_t)W * (REC * 8 + HEAD) * 2 + (size_t)W * W * 8 + 8192));
+    unsigned long long *rec_all = ptr<unsigned long long>(c->sh_small);            // [W][REC]
+    unsigned long long *rec_mine = rec_all + (size_t)W * REC;                      // [REC]
+    uint8_t *heads_all = reinterpret_cast<uint8_t *>(rec_mine + REC);              // [W][HEAD]
+    unsigned long long *cntmat = reinterpret_cast<unsigned long long *>(heads_all + (((size_t)W * HEAD + 63) & ~(size_t)63));   // [W][W] send counts
+    unsigned long long *cnt_mine = cntmat + (size_t)W * W;                         // [W]
+    unsigned long long *h64 = cnt_mine + W;                                        // [768]
+    TRY(mark(c, "shard_edges"));
+    // record: len, first, last  (+ head bytes)
+    {
+        unsigned long long h_rec[REC] = {len, 0, 0, 0, 0, 0, 0, cap};        // [7]: output capacity, so that every rank can
+                                                                            // see every rank's fit and all fail together
+        CU_TRY(c, cudaMemcpyAsync(rec_mine, h_rec, sizeof h_rec, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaMemsetAsync(heads_all + (size_t)R * HEAD, 0, HEAD, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(heads_all + (size_t)R * HEAD, d_shard, len < HEAD ? len : HEAD, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(reinterpret_cast<uint8_t *>(rec_mine + 1), d_shard, 1, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(reinterpret_cast<uint8_t *>(rec_mine + 2), d_shard + len - 1, 1, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    std::vector<unsigned long long> hrec((size_t)W * REC);
+    std::vector<uint8_t> hheads((size_t)W * HEAD);
+    auto gather_records = [&]() -> int {
+        if (W > 1) {
+            NCCL_TRY(c, N.AllGather(rec_mine, rec_all, REC, ncclUint64, c->comm, c->stream));
+        } else {
+            CU_TRY(c, cudaMemcpyAsync(rec_all, rec_mine, REC * 8, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        CU_TRY(c, cudaMemcpyAsync(hrec.data(), rec_all, (size_t)W * REC * 8, cudaMemcpyDeviceToHost, c->stream));
+        return B200SA_OK;
+    };
+    TRY(gather_records());
+    if (W > 1) NCCL_TRY(c, N.AllGather(heads_all + (size_t)R * HEAD, heads_all, HEAD, ncclUint8, c->comm, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(hheads.data(), heads_all, (size_t)W * HEAD, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    uint64_t lo = 0, n_total = 0;
+    for (int r = 0; r < W; r++) { if (r < R) lo += hrec[r * REC]; n_total += hrec[r * REC]; }
+    int next_char = -1, prev_char = -1;
+    if (R + 1 < W) next_char = (int)(hrec[(R + 1) * REC + 1] & 0xff);
+    if (R > 0) prev_char = (int)(hrec[(R - 1) * REC + 2] & 0xff);
+    // halo: the bytes that follow this shard, taken from the heads of the following shards
+    std::vector<uint8_t> halo;                     // up to HEAD bytes (or everything up to the end of the text)
+    for (int r = R + 1; r < W && halo.size() < (size_t)HEAD; r++) {
+        uint64_t take = hrec[r * REC] < (uint64_t)HEAD ? hrec[r * REC] : (uint64_t)HEAD;
+        halo.insert(halo.end(), hheads.begin() + (size_t)r * HEAD, hheads.begin() + (size_t)r * HEAD + take);
+    }
+    if (halo.size() > (size_t)HEAD) halo.resize(HEAD);
+    // ---- shard state -> tail carries
+    TRY(mark(c, "shard_classify"));
+    int state = ST_L;
+    if (next_char >= 0) {
+        uint64_t nw = (len + 31) / 32;
+        uint32_t nbc = cdiv(nw, CLS_WORDS);
+        TRY(ensure(c, c->blkstate, nbc));
+        TRY(ensure(c, c->carry, nbc));
+        ShardEdge e0{next_char, -1, ST_P};
+        LAUNCH(c, k_cls_block_state, nbc, d_shard, len, ptr<uint8_t>(c->blkstate), e0);
+        LAUNCH(c, k_cls_carry, 1, ptr<uint8_t>(c->blkstate), nbc, ptr<uint8_t>(c->carry), (uint32_t)ST_P);
+        uint8_t h2[2];
+        CU_TRY(c, cudaMemcpyAsync(&h2[0], c->blkstate.p, 1, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(&h2[1], c->carry.p, 1, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        state = (h2[0] != ST_P) ? h2[0] : h2[1];
+    }
+    {
+        unsigned long long st = (unsigned long long)state;
+        CU_TRY(c, cudaMemcpyAsync(rec_mine + 3, &st, 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(gather_records());
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    uint32_t tail = ST_L;
+    for (int r = R + 1; r < W; r++) if (hrec[r * REC + 3] != ST_P) { tail = (uint32_t)hrec[r * REC + 3]; break; }
+    // ---- classification of the shard (fused kernel with halo chars), LMS positions descending
+    uint32_t m = 0;
+    TRY(classify_fused_dev(c, d_shard, len, &m, ShardEdge{next_char, prev_char, next_char >= 0 ? tail : ST_L}, false));
+    // ---- global alphabet: all-reduce of the (byte, type) histogram
+    TRY(mark(c, "shard_keys"));
+    uint32_t *tab = ptr<uint32_t>(c->tables);
+    LAUNCH(c, k_hist_to_u64, 3u, tab + T_HIST, h64, 768u);
+    if (W > 1) NCCL_TRY(c, N.AllReduce(h64, h64, 768, ncclUint64, ncclSum, c->comm, c->stream));
+    uint32_t *sm = ptr<uint32_t>(c->small);
+    LAUNCH(c, k_alpha_from_hist64, 1u, h64, tab + T_CODE, sm + 3);
+    TRY(read_words(c, sm + 3, 1));
+    const uint32_t sigma = c->h_pin[0] < 2 ? 2u : c->h_pin[0];
+    uint32_t kc = 0;
+    {
+        unsigned __int128 r = 1;
+        while (kc < 32 && r * sigma <= ((unsigned __int128)1 << 64)) { r *= sigma; kc++; }
+    }
+    // ---- window keys of the local LMS suffixes (descending position order)
+    TRY(ensure(c, c->sh_a, (size_t)(m + 1) * 8));                 // keys
+    TRY(ensure(c, c->sh_b, (size_t)(m + 1) * 4));                 // local positions
+    TRY(ensure(c, c->sh_c, (size_t)(m + 1) * 8));                 // keys partitioned by destination
+    TRY(ensure(c, c->sh_d, (size_t)(m + 1) * 4));                 // positions partitioned
+    TRY(ensure(c, c->flag, (size_t)m + 64 + HEAD));               // destinations (+ halo bytes at the end)
+    uint8_t *d_halo = ptr<uint8_t>(c->flag) + (((size_t)m + 15) & ~(size_t)15);
+    if (!halo.empty()) CU_TRY(c, cudaMemcpyAsync(d_halo, halo.data(), halo.size(), cudaMemcpyHostToDevice, c->stream));
+    ShardWin SW{d_shard, d_halo, tab + T_CODE, len, (uint64_t)halo.size(), sigma, kc};
+    uint64_t *K0 = ptr<uint64_t>(c->sh_a), *K1 = ptr<uint64_t>(c->sh_c);
+    uint32_t *V0 = ptr<uint32_t>(c->sh_b), *V1 = ptr<uint32_t>(c->sh_d);
+    if (m) LAUNCH(c, k_shard_keys, cdiv(m, BLK), SW, ptr<uint32_t>(c->lmsdesc), m, K0, V0);
+    // ---- splitters from an all-gathered sample
+    TRY(mark(c, "shard_partition"));
+    const uint32_t PER = 1024;
+    TRY(ensure(c, c->sh_e, (size_t)W * PER * 8 * 2 + (size_t)W * PER * 4 * 2 + 256));
+    uint64_t *samp = ptr<uint64_t>(c->sh_e), *samp2 = samp + (size_t)W * PER;
+    uint32_t *sv0 = reinterpret_cast<uint32_t *>(samp2 + (size_t)W * PER), *sv1 = sv0 + (size_t)W * PER;
+    uint64_t *split = reinterpret_cast<uint64_t *>(sv1 + (size_t)W * PER);
+    LAUNCH(c, k_shard_sample, cdiv(PER, BLK), K0, m, PER, samp + (size_t)R * PER);
+    if (W > 1) NCCL_TRY(c, N.AllGather(samp + (size_t)R * PER, samp, PER, ncclUint64, c->comm, c->stream));
+    {
+        uint64_t *ks; uint32_t *vs;
+        LAUNCH(c, k_iota, cdiv(W * PER, BLK), sv0, (uint32_t)(W * PER));
+        TRY(sort_pairs<uint64_t>(c, samp, sv0, samp2, sv1, (uint64_t)W * PER, 64, &ks, &vs));
+        LAUNCH(c, k_shard_splitters, 1u, ks, (uint32_t)(W * PER), (uint32_t)W, split);
+    }
+    CU_TRY(c, cudaMemsetAsync(cnt_mine, 0, (size_t)W * 8, c->stream));
+    uint8_t *dest = ptr<uint8_t>(c->flag);
+    if (m) {
+        LAUNCH(c, k_shard_dest, cdiv(m, BLK), K0, m, split, (uint32_t)W, dest, cnt_mine);
+        TRY(radix_pass(c, DigU8{dest}, MoveKV64{K0, V0, K1, V1}, m));        // stable: descending position inside a destination
+    }
+    if (W > 1) NCCL_TRY(c, N.AllGather(cnt_mine, cntmat, W, ncclUint64, c->comm, c->stream));
+    else CU_TRY(c, cudaMemcpyAsync(cntmat, cnt_mine, 8, cudaMemcpyDeviceToDevice, c->stream));
+    std::vector<unsigned long long> hcnt((size_t)W * W);
+    CU_TRY(c, cudaMemcpyAsync(hcnt.data(), cntmat, (size_t)W * W * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    // ---- all-to-all: chunks are received in DESCENDING source rank (larger text positions first)
+    TRY(mark(c, "shard_exchange"));
+    uint64_t recv_total = 0, m_total = 0;
+    std::vector<uint64_t> roff(W + 1, 0), soff(W + 1, 0);
+    for (int k = 0; k < W; k++) { int src = W - 1 - k; roff[k + 1] = roff[k] + hcnt[(size_t)src * W + R]; }
+    for (int d = 0; d < W; d++) soff[d + 1] = soff[d] + hcnt[(size_t)R * W + d];
+    recv_total = roff[W];
+    for (int r = 0; r < W; r++) for (int d = 0; d < W; d++) m_total += hcnt[(size_t)r * W + d];
+    for (int r = 0; r < W; r++) {                  // the same verdict on every rank: nobody enters the exchange alone
+        uint64_t slice = 0;
+        for (int q = 0; q < W; q++) slice += hcnt[(size_t)q * W + r];
+        if (slice > 0xfffffff0ull) { c->last_error = "more than 2^32 LMS suffixes on one rank"; return B200SA_ERR_TOO_LARGE; }
+        if (slice > hrec[r * REC + 7]) {
+            char b[160]; snprintf(b, sizeof b, "output capacity of rank %d too small for its slice (%llu entries)", r, (unsigned long long)slice);
+            c->last_error = b; return B200SA_ERR_BAD_ARG;
+        }
+    }
+    TRY(ensure(c, c->sh_a, (size_t)(recv_total + 1) * 8));         // received keys (K0 is free after the partition)
+    TRY(ensure(c, c->sh_b, (size_t)(recv_total + 1) * 4));         // received local positions
+    K0 = ptr<uint64_t>(c->sh_a); V0 = ptr<uint32_t>(c->sh_b);
+    if (W > 1) {
+        NCCL_TRY(c, N.GroupStart());
+        for (int k = 0; k < W; k++) {
+            int src = W - 1 - k;
+            uint64_t cnt = roff[k + 1] - roff[k];
+            if (cnt) {
+                NCCL_TRY(c, N.Recv(K0 + roff[k], cnt, ncclUint64, src, c->comm, c->stream));
+                NCCL_TRY(c, N.Recv(V0 + roff[k], cnt, ncclUint32, src, c->comm, c->stream));
+            }
+        }
+        for (int d = 0; d < W; d++) {
+            uint64_t cnt = soff[d + 1] - soff[d];
+            if (cnt) {
+                NCCL_TRY(c, N.Send(K1 + soff[d], cnt, ncclUint64, d, c->comm, c->stream));
+                NCCL_TRY(c, N.Send(V1 + soff[d], cnt, ncclUint32, d, c->comm, c->stream));
+                if (d != R) { out->bytes_sent += (double)cnt * 12.0; }
+            }
+        }
+        NCCL_TRY(c, N.GroupEnd());
+    } else if (recv_total) {
+        CU_TRY(c, cudaMemcpyAsync(K0, K1, recv_total * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(V0, V1, recv_total * 4, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    // ---- local sort of the received slice, global positions, groups, names
+    TRY(mark(c, "shard_sort"));
+    uint32_t cnt32 = (uint32_t)recv_total;
+    TRY(ensure(c, c->sh_c, (size_t)(recv_total + 1) * 8));
+    TRY(ensure(c, c->sh_d, (size_t)(recv_total + 1) * 4));
+    TRY(ensure(c, c->sh_f, (size_t)(recv_total + 1) * 4));
+    uint32_t *I0 = ptr<uint32_t>(c->sh_d), *I1 = ptr<uint32_t>(c->sh_f);
+    uint64_t *Ks = K0; uint32_t *Is = I0;
+    unsigned long long *chunk_off = cnt_mine;                      // reuse: [W+1] offsets, then [W] lo
+    std::vector<unsigned long long> hco((size_t)2 * W + 1);
+    for (int k = 0; k <= W; k++) hco[k] = roff[k];
+    for (int k = 0; k < W; k++) { int src = W - 1 - k; uint64_t l2 = 0; for (int r = 0; r < src; r++) l2 += hrec[r * REC]; hco[W + 1 + k] = l2; }
+    TRY(ensure(c, c->sh_e, (size_t)(2 * W + 1) * 8 + 64));
+    chunk_off = ptr<unsigned long long>(c->sh_e);
+    CU_TRY(c, cudaMemcpyAsync(chunk_off, hco.data(), hco.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    unsigned long long *d_ties = h64;                              // reuse (the histogram is consumed)
+    CU_TRY(c, cudaMemsetAsync(d_ties, 0, 16, c->stream));
+    if (cnt32) {
+        LAUNCH(c, k_iota, cdiv(cnt32, BLK), I0, cnt32);
+        int kbits = 64;
+        TRY(sort_pairs<uint64_t>(c, K0, I0, ptr<uint64_t>(c->sh_c), I1, cnt32, kbits, &Ks, &Is));
+        LAUNCH(c, k_shard_gpos, cdiv(cnt32, BLK), Is, V0, cnt32, chunk_off, chunk_off + W + 1, (uint32_t)W, d_sorted_gpos);
+        InShardHead in{Ks, d_sorted_gpos, cnt32, n_total, kc};
+        TRY((dev_scan<OpSum>(c, in, OutShardName{in, 0u, d_names, d_ties}, cnt32, sm + 16)));
+    } else {
+        CU_TRY(c, cudaMemsetAsync(sm + 16, 0, 4, c->stream));
+    }
+    // ---- name offsets: exclusive prefix of the distinct counts over ranks; ties summed
+    TRY(mark(c, "shard_names"));
+    CU_TRY(c, cudaMemcpyAsync(reinterpret_cast<uint32_t *>(rec_mine + 5), sm + 16, 4, cudaMemcpyDeviceToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(rec_mine + 6, d_ties, 8, cudaMemcpyDeviceToDevice, c->stream));
+    {
+        unsigned long long mm = m;
+        CU_TRY(c, cudaMemcpyAsync(rec_mine + 4, &mm, 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    TRY(gather_records());
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    uint64_t name_off = 0, ties = 0;
+    for (int r = 0; r < W; r++) { if (r < R) name_off += (uint32_t)hrec[r * REC + 5]; ties += hrec[r * REC + 6]; }
+    if (cnt32 && name_off) LAUNCH(c, k_add_u32, cdiv(cnt32, BLK), d_names, cnt32, (uint32_t)name_off);
+    TRY(mark(c, "end"));
+    CU_TRY(c, cudaGetLastError());
+    out->n_total = n_total; out->m_total = m_total; out->m_local = m; out->recv_count = recv_total;
+    out->distinct_local = (uint32_t)hrec[R * REC + 5]; out->name_offset = name_off; out->ties_total = ties;
+    out->kc = kc; out->lo = lo; out->nranks = (uint32_t)W; out->rank = (uint32_t)R;
+    out->bytes_recv = 0;
+    for (int k = 0; k < W; k++) { int src = W - 1 - k; if (src != R) out->bytes_recv += (double)(roff[k + 1] - roff[k]) * 12.0; }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
     return end_call(c);
 }
 

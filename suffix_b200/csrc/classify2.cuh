@@ -66,6 +66,16 @@ __device__ __forceinline__ uint32_t resolve_types(uint32_t lt, uint32_t gt, uint
     return __brev(v);
 }
 
+constexpr uint32_t HIST_COPIES = 64;
+// hist[k] = sum of the interleaved copies
+__global__ void __launch_bounds__(BLK) k_hist_fold(const uint32_t *__restrict__ copies, uint32_t *hist) {
+    for (uint32_t k = threadIdx.x; k < 768; k += BLK) {
+        uint32_t v = 0;
+        for (uint32_t q = 0; q < HIST_COPIES; q++) v += copies[(size_t)q * 768u + k];
+        hist[k] = v;
+    }
+}
+
 struct Cls2State {
     uint32_t *state;     // [tiles] epoch-tagged: tag + 1 + {ST_L, ST_S, ST_P}
     uint32_t tag;        // distinct per call
@@ -174,11 +184,16 @@ __global__ void __launch_bounds__(BLK) k_classify_fused(const uint8_t *__restric
         }
     }
     __syncthreads();
-    for (int k = tid; k < 768; k += BLK) {
-        uint32_t v = 0;
+    // 12 k tiles adding to the same few global words serialise in L2 (measured: 47 % of this
+    // kernel's stall samples); HIST_COPIES interleaved copies are summed by k_hist_fold
+    {
+        uint32_t *hcopy = hist768 + (size_t)(tile % HIST_COPIES) * 768u;
+        for (int k = tid; k < 768; k += BLK) {
+            uint32_t v = 0;
 #pragma unroll
-        for (int ww = 0; ww < NWARP; ww++) v += s_hist[ww][k];
-        if (v) atomicAdd(&hist768[k], v);
+            for (int ww = 0; ww < NWARP; ww++) v += s_hist[ww][k];
+            if (v) atomicAdd(&hcopy[k], v);
+        }
     }
     if (lmspos_desc) {
         const uint32_t base = s_prefix;

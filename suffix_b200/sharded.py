@@ -110,3 +110,53 @@ def classify_sharded(engine, shard, dist=None, device=None):
     return ShardResult(lo=lo, stype_words=stype, lms_words=lms, lmspos_local=lmspos, m_local=m,
                        m_offset=sum(ms[:rank]), m_total=sum(ms), hist_global=h.cpu().numpy().astype(np.uint64),
                        state=state, tail_carry=tail)
+
+
+# ---------------------------------------------------------------------------------------
+# Sharded LMS-suffix sort (BASELINE config 5): the collectives run
+# INSIDE the library (NCCL behind the C-ABI, b200sa_shard_lms_sort); Python only hands
+# the 128-byte NCCL unique id from rank 0 to the other ranks.
+_comm_ready = {}
+
+
+def ensure_comm(ctx, dist=None):
+    """Creates the library-side communicator of `ctx` once (rank / world of torch.distributed)."""
+    key = id(ctx)
+    if key in _comm_ready:
+        return
+    if dist is None or dist.get_world_size() == 1:
+        _comm_ready[key] = True
+        return
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", ctx.device)
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(uid, src=0)
+    ctx.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    _comm_ready[key] = True
+
+
+def lms_sort_sharded(ctx, shard, dist=None, cap=None):
+    """Collective: every rank passes its contiguous shard (a CUDA uint8 tensor, rank order = text
+    order).  Returns (gpos, names, stats): this rank's slice of the LMS suffixes of the whole text
+    ordered by their first `stats['kc']` characters (int64 global positions), the dense global
+    window names, and the statistics of b200sa_shard_stats.  stats['ties_total'] == 0 means the
+    concatenated slices are the LMS suffixes in exact suffix order."""
+    import torch
+    ensure_comm(ctx, dist)
+    n = shard.numel()
+    if cap is None:                      # slices are balanced by the sampled splitters: ~ m_total / world entries
+        tot = torch.tensor([n], dtype=torch.int64, device=shard.device)
+        if dist is not None and dist.get_world_size() > 1:
+            dist.all_reduce(tot)
+        world = dist.get_world_size() if dist is not None else 1
+        cap = int(tot.item()) // 2 // world * 2 + 65536 if world > 1 else n // 2 + 4096
+    cap = int(cap)
+    gpos = torch.empty(cap, dtype=torch.int64, device=shard.device)
+    names = torch.empty(cap, dtype=torch.int32, device=shard.device)
+    st = ctx.shard_lms_sort(shard.data_ptr(), n, gpos.data_ptr(), names.data_ptr(), cap,
+                            torch.cuda.current_stream().cuda_stream)
+    k = int(st["recv_count"])
+    return gpos[:k], names[:k], st

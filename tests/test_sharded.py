@@ -159,3 +159,118 @@ def test_sharded_nccl_two_gpus():
     for p in procs:
         p.join(timeout=60)
     assert res == {0: True, 1: True}
+
+
+# ---------------------------------------------------------------------------------------
+# sharded LMS-suffix sort: numpy mirror under gloo; the CUDA + NCCL
+# product path on one and two GPUs
+def _sorted_lms_oracle(t):
+    ty = oracle.types(t)
+    sa = oracle.sais(t)
+    return sa[ty[sa] == 2].astype(np.int64)
+
+
+def _check_global_order(t, gpos_all, names_all, ties, kc):
+    want = _sorted_lms_oracle(t)
+    assert len(gpos_all) == len(want)
+    assert sorted(gpos_all.tolist()) == sorted(want.tolist())
+    tb = t.tobytes()
+    win = [tb[p:p + kc] for p in gpos_all.tolist()]
+    assert all(win[i] <= win[i + 1] for i in range(len(win) - 1))          # ordered by the first kc bytes
+    nm = names_all.tolist()
+    assert all(0 <= nm[i + 1] - nm[i] <= 1 for i in range(len(nm) - 1)) and (not nm or nm[0] == 0)
+    if ties == 0:
+        assert np.array_equal(gpos_all, want)                                # exact suffix order
+        assert nm == list(range(len(nm)))
+
+
+def _lms_worker(rank, world, port, texts, cutsets, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.shard_ref import lms_sort_sharded_model
+    out = []
+    for t, cuts in zip(texts, cutsets):
+        g, nm, st = lms_sort_sharded_model(t[cuts[rank]:cuts[rank + 1]], dist)
+        out.append((g, nm, st["ties_total"], st["kc"]))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_lms_sort_model_gloo(world):
+    rng = np.random.default_rng(50 + world)
+    texts = [np.frombuffer(d, dtype=np.uint8) for nm_, d in families.adversarial() if 8 <= len(d) <= 12000][:14]
+    texts += [gen.dna(30_000), gen.rand_bytes(8_000), gen.english(9_000), gen.dna(2_001, newline_tail=True)]
+    cutsets = [_cuts(len(t), world, rng) for t in texts]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lms_worker, args=(r, world, port, texts, cutsets, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    for k, t in enumerate(texts):
+        g = np.concatenate([res[r][k][0] for r in range(world)])
+        nm = np.concatenate([res[r][k][1] for r in range(world)])
+        _check_global_order(t, g, nm, res[0][k][2], res[0][k][3])
+
+
+@pytest.mark.gpu
+def test_sharded_lms_sort_cuda_world1():
+    """b200sa_shard_lms_sort on one GPU (a world of 1: same kernels, self-exchange)."""
+    from suffix_b200 import _lib
+    ctx = _lib.Context(0)
+    cases = [gen.dna(3_000_000), gen.dna(500_001, newline_tail=True), gen.rand_bytes(1_000_000), gen.english(400_000),
+             gen.fixture("AP009048_100000.fasta")]
+    cases += [np.frombuffer(d, dtype=np.uint8) for _, d in families.adversarial() if len(d) >= 64]
+    for t in cases:
+        d_t = torch.from_numpy(np.ascontiguousarray(t).copy()).cuda()
+        g, nm, st = sharded.lms_sort_sharded(ctx, d_t)
+        torch.cuda.synchronize()
+        assert st["n_total"] == len(t) and st["m_total"] == st["recv_count"] == g.numel()
+        _check_global_order(np.ascontiguousarray(t), g.cpu().numpy(), nm.cpu().numpy().astype(np.int64), st["ties_total"], st["kc"])
+    ctx.close()
+
+
+def _nccl_lms_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from suffix_b200 import _lib
+    ctx = _lib.Context(rank)
+    out = []
+    for t, cuts in ((gen.dna(4_000_000), [0, 1_999_984, 4_000_000]), (gen.rand_bytes(600_000), [0, 16, 600_000]),
+                    (gen.dna(300_001, newline_tail=True), [0, 299_984, 300_001])):
+        shard = torch.from_numpy(t[cuts[rank]:cuts[rank + 1]].copy()).cuda()
+        g, nm, st = sharded.lms_sort_sharded(ctx, shard, dist=dist, cap=len(t) // 2 + 4096)
+        torch.cuda.synchronize()
+        out.append((g.cpu().numpy(), nm.cpu().numpy().astype(np.int64), st["ties_total"], st["kc"], st["bytes_sent"]))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_lms_sort_nccl_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_lms_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    texts = [gen.dna(4_000_000), gen.rand_bytes(600_000), gen.dna(300_001, newline_tail=True)]
+    for k, t in enumerate(texts):
+        g = np.concatenate([res[r][k][0] for r in range(2)])
+        nm = np.concatenate([res[r][k][1] for r in range(2)])
+        _check_global_order(t, g, nm, res[0][k][2], res[0][k][3])
+        assert res[0][k][4] > 0 or res[1][k][4] > 0          # something crossed NVLink
