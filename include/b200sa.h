@@ -118,6 +118,26 @@ int b200sa_shard_classify(b200sa_ctx *ctx, const uint8_t *d_shard, uint64_t len,
                           int tail_carry, uint32_t *d_stype_words, uint32_t *d_lms_words,
                           uint32_t *d_lmspos, uint64_t cap_lms, uint64_t *hist768, uint64_t *m_out, void *stream);
 
+/* ---- generalized suffix array (reference README.md:60-74, TODO:13-18) ----
+ * The reference's own recipe: append the documents with a separator byte that occurs in none
+ * of them, remember where each starts, build ONE SuffixTable, and map a match position back
+ * to its document with a binary search.  This entry point does that mapping for a batch of
+ * positions on the device: doc_starts[0..ndocs) ascending (doc_starts[0] = 0), a position p
+ * belongs to the last document d with doc_starts[d] <= p; d_off = p - doc_starts[d].
+ * (suffix_b200.GeneralizedSuffixTable is the host-side wrapper.) */
+int b200sa_doc_ids_dev(b200sa_ctx *ctx, const uint32_t *d_pos, uint64_t count,
+                       const uint32_t *d_doc_starts, uint32_t ndocs,
+                       uint32_t *d_doc, uint32_t *d_off, void *stream);
+
+/* ---- LCP-interval tree (reference suffix_tree/src/lib.rs:392-505) ----
+ * The internal nodes of the suffix tree the reference builds serially from SA + LCP are the
+ * LCP intervals.  For every rank i: d_psv[i] = largest j < i with lcp[j] < lcp[i]
+ * (0xFFFFFFFF if none), d_nsv[i] = smallest j > i with lcp[j] < lcp[i] (n if none); the
+ * node that owns the boundary between suffixes i-1 and i is the interval
+ * [psv[i], nsv[i]) of string depth lcp[i] (all-nearest-smaller-values over block minima). */
+int b200sa_lcp_intervals_dev(b200sa_ctx *ctx, const uint32_t *d_lcp, uint64_t n,
+                             uint32_t *d_psv, uint32_t *d_nsv, void *stream);
+
 /* ---- multi-GPU: communicator + sharded LMS-suffix sort ----
  * One process (or thread) and one context per GPU.  NCCL is resolved at run time
  * (the copy already loaded in the process, else libnccl.so.2); the single-GPU entry
@@ -161,6 +181,15 @@ int b200sa_comm_destroy(b200sa_ctx *ctx);
 int b200sa_shard_lms_sort(b200sa_ctx *ctx, const uint8_t *d_shard, uint64_t len,
                           unsigned long long *d_sorted_gpos, uint32_t *d_names, uint64_t cap,
                           b200sa_shard_stats *out, void *stream);
+
+/* Sharded lcp_lens (collective): d_text (n bytes), d_sa and d_lcp (n u32) are
+ * device buffers on EVERY rank.  replicated == 0: rank 0 holds text and table, they are
+ * broadcast first; != 0: every rank already holds them.  Every rank computes Phi / PLCP for
+ * its own range of text positions, the ranges are all-gathered, every rank turns its range of
+ * ranks into LCP values, the slices are all-gathered: on return every rank holds the whole
+ * lcp array, equal to lcp_lens_quadratic(text, table) (src/table.rs:348-361). */
+int b200sa_lcp_sharded(b200sa_ctx *ctx, uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint32_t *d_lcp,
+                       int replicated, void *stream);
 
 /* ---- introspection (bench / tests) ---- */
 

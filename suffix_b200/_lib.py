@@ -60,6 +60,9 @@ def lib():
         "b200sa_comm_attach": ([vp, vp], ci),
         "b200sa_comm_destroy": ([vp], ci),
         "b200sa_shard_lms_sort": ([vp, vp, u64, vp, vp, u64, ctypes.POINTER(ShardStats), vp], ci),
+        "b200sa_doc_ids_dev": ([vp, vp, u64, vp, u32, vp, vp, vp], ci),
+        "b200sa_lcp_intervals_dev": ([vp, vp, u64, vp, vp, vp], ci),
+        "b200sa_lcp_sharded": ([vp, vp, u64, vp, vp, ci, vp], ci),
         "b200sa_last_stats": ([vp, ctypes.POINTER(Stats)], ci),
         "b200sa_set_timing": ([vp, ci], ci),
         "b200sa_last_phase_times": ([vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ci], ci),
@@ -180,6 +183,15 @@ class Context:
         st = ShardStats()
         self._check(lib().b200sa_shard_lms_sort(self._h, d_shard, length, d_gpos, d_names, cap, ctypes.byref(st), stream))
         return {f: getattr(st, f) for f, _ in ShardStats._fields_}
+
+    def doc_ids_dev(self, d_pos: int, count: int, d_doc_starts: int, ndocs: int, d_doc: int, d_off: int, stream: int = 0):
+        self._check(lib().b200sa_doc_ids_dev(self._h, d_pos, count, d_doc_starts, ndocs, d_doc, d_off, stream))
+
+    def lcp_intervals_dev(self, d_lcp: int, n: int, d_psv: int, d_nsv: int, stream: int = 0):
+        self._check(lib().b200sa_lcp_intervals_dev(self._h, d_lcp, n, d_psv, d_nsv, stream))
+
+    def lcp_sharded(self, d_text: int, n: int, d_sa: int, d_lcp: int, replicated: bool = False, stream: int = 0):
+        self._check(lib().b200sa_lcp_sharded(self._h, d_text, n, d_sa, d_lcp, 1 if replicated else 0, stream))
 
     # ---- introspection
     def set_timing(self, on: bool):

@@ -1038,13 +1038,13 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
     uint32_t pg = cdiv(nchunk, BLK), sg = cdiv(cdiv(nchunk, 32), BLK);
     TRY(ensure(c, c->plcp_samp, (size_t)nchunk * 4));
     uint32_t *samp = ptr<uint32_t>(c->plcp_samp), *phi = ptr<uint32_t>(c->isa);
-    if (c->bits == 2) LAUNCH(c, (k_plcp_samples<2>), sg, c->ptext, n32, phi, samp);
-    else if (c->bits == 4) LAUNCH(c, (k_plcp_samples<4>), sg, c->ptext, n32, phi, samp);
-    else LAUNCH(c, (k_plcp_samples<8>), sg, c->ptext, n32, phi, samp);
+    if (c->bits == 2) LAUNCH(c, (k_plcp_samples<2>), sg, c->ptext, n32, phi, samp, (uint64_t)0, ~(uint64_t)0);
+    else if (c->bits == 4) LAUNCH(c, (k_plcp_samples<4>), sg, c->ptext, n32, phi, samp, (uint64_t)0, ~(uint64_t)0);
+    else LAUNCH(c, (k_plcp_samples<8>), sg, c->ptext, n32, phi, samp, (uint64_t)0, ~(uint64_t)0);
     TRY(mark(c, "lcp_plcp_fill"));
-    if (c->bits == 2) LAUNCH(c, (k_plcp<2>), pg, c->ptext, n32, phi, samp);
-    else if (c->bits == 4) LAUNCH(c, (k_plcp<4>), pg, c->ptext, n32, phi, samp);
-    else LAUNCH(c, (k_plcp<8>), pg, c->ptext, n32, phi, samp);
+    if (c->bits == 2) LAUNCH(c, (k_plcp<2>), pg, c->ptext, n32, phi, samp, (uint64_t)0, ~(uint64_t)0);
+    else if (c->bits == 4) LAUNCH(c, (k_plcp<4>), pg, c->ptext, n32, phi, samp, (uint64_t)0, ~(uint64_t)0);
+    else LAUNCH(c, (k_plcp<8>), pg, c->ptext, n32, phi, samp, (uint64_t)0, ~(uint64_t)0);
     TRY(mark(c, "lcp_gather"));
     LAUNCH(c, k_lcp_gather, cdiv(n, BLK), d_sa, ptr<uint32_t>(c->isa), n32, d_lcp);
     TRY(mark(c, "end"));
@@ -1383,6 +1383,44 @@ int b200sa_shard_classify(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, i
     return end_call(c);
 }
 
+// ------------------------------------------------------------ generalized SA / LCP intervals
+int b200sa_doc_ids_dev(b200sa_ctx *c, const uint32_t *d_pos, uint64_t count, const uint32_t *d_doc_starts,
+                       uint32_t ndocs, uint32_t *d_doc, uint32_t *d_off, void *stream) {
+    if (!c || ndocs < 1 || !d_doc_starts || (count > 0 && (!d_pos || !d_doc || !d_off))) return B200SA_ERR_BAD_ARG;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    if (count) LAUNCH(c, k_doc_ids, cdiv(count, BLK), d_pos, count, d_doc_starts, ndocs, d_doc, d_off);
+    CU_TRY(c, cudaGetLastError());
+    return end_call(c);
+}
+
+int b200sa_lcp_intervals_dev(b200sa_ctx *c, const uint32_t *d_lcp, uint64_t n, uint32_t *d_psv, uint32_t *d_nsv,
+                             void *stream) {
+    if (!c || (n > 0 && (!d_lcp || !d_psv || !d_nsv))) return B200SA_ERR_BAD_ARG;
+    if (n > B200SA_MAX_N) return B200SA_ERR_TOO_LARGE;
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    if (n == 0) return end_call(c);
+    AnsvLevels L;
+    memset(&L, 0, sizeof L);
+    L.lv[0] = d_lcp; L.cnt[0] = n; L.nlev = 1;
+    uint64_t total = 0;
+    for (uint64_t k = (n + 31) / 32; ; k = (k + 31) / 32) { total += k; if (k <= 32) break; }
+    TRY(ensure(c, c->qbuf, (total + 64) * 4));
+    uint32_t *lvbuf = ptr<uint32_t>(c->qbuf);
+    uint64_t cnt = n;
+    while (cnt > 32 && L.nlev < 8) {
+        uint64_t nxt = (cnt + 31) / 32;
+        LAUNCH(c, k_min32, cdiv(nxt, BLK), L.lv[L.nlev - 1], cnt, lvbuf);
+        L.lv[L.nlev] = lvbuf; L.cnt[L.nlev] = nxt; L.nlev++;
+        lvbuf += nxt;
+        cnt = nxt;
+    }
+    LAUNCH(c, k_ansv, cdiv(n, BLK), L, n, d_psv, d_nsv);
+    CU_TRY(c, cudaGetLastError());
+    return end_call(c);
+}
+
 // ------------------------------------------------------------ multi-GPU: communicator + sharded LMS sort
 #define NCCL_TRY(ctx, expr)                                                                  \
     do {                                                                                     \
@@ -1669,6 +1707,88 @@ int b200sa_shard_lms_sort(b200sa_ctx *c, const uint8_t *d_shard, uint64_t len, u
     out->kc = kc; out->lo = lo; out->nranks = (uint32_t)W; out->rank = (uint32_t)R;
     out->bytes_recv = 0;
     for (int k = 0; k < W; k++) { int src = W - 1 - k; if (src != R) out->bytes_recv += (double)(roff[k + 1] - roff[k]) * 12.0; }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return end_call(c);
+}
+
+// Sharded LCP: text and SA are replicated (broadcast from rank 0 unless the caller
+// says they already are), every rank computes Phi and PLCP for ITS text range only, the PLCP ranges
+// are all-gathered, every rank turns its rank range into LCP values and the slices are all-gathered.
+// Same values as lcp_lens_quadratic (src/table.rs:348-361).
+int b200sa_lcp_sharded(b200sa_ctx *c, uint8_t *d_text, uint64_t n, uint32_t *d_sa, uint32_t *d_lcp, int replicated,
+                       void *stream) {
+    if (!c || (n > 0 && (!d_text || !d_sa || !d_lcp))) return B200SA_ERR_BAD_ARG;
+    if (n > B200SA_MAX_N) return B200SA_ERR_TOO_LARGE;
+    NcclApi &N = nccl_api();
+    const int W = c->comm ? c->nranks : 1, R = c->comm ? c->comm_rank : 0;
+    if (W > 1 && !N.ok) { c->last_error = N.err; return B200SA_ERR_COMM; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    begin_call(c, stream);
+    if (n == 0) return end_call(c);
+    if (((uintptr_t)d_text & 15) != 0) { c->last_error = "text pointer must be 16-byte aligned"; return B200SA_ERR_BAD_ARG; }
+    const uint32_t n32 = (uint32_t)n;
+    TRY(mark(c, "lcps_bcast"));
+    if (W > 1 && !replicated) {
+        NCCL_TRY(c, N.Broadcast(d_text, d_text, n, ncclUint8, 0, c->comm, c->stream));
+        NCCL_TRY(c, N.Broadcast(d_sa, d_sa, n, ncclUint32, 0, c->comm, c->stream));
+    }
+    // ---- every rank: validate the table, pack the text (same steps as the stand-alone b200sa_lcp_dev)
+    TRY(mark(c, "lcps_pack"));
+    const uint64_t per = ((n + W - 1) / W + 1023) / 1024 * 1024;       // positions (and ranks) per GPU
+    TRY(ensure(c, c->isa, (size_t)W * per * 4));
+    TRY(ensure(c, c->small, 4096));
+    TRY(ensure(c, c->tables, T_END * 4));
+    uint32_t *tab = ptr<uint32_t>(c->tables), *sm = ptr<uint32_t>(c->small);
+    {
+        uint64_t nwv = (n + 31) / 32;
+        uint32_t *seen = ptr<uint32_t>(c->isa), *bad = sm + 12;
+        CU_TRY(c, cudaMemsetAsync(seen, 0, nwv * 4, c->stream));
+        CU_TRY(c, cudaMemsetAsync(bad, 0, 4, c->stream));
+        LAUNCH(c, k_sa_validate, cdiv(n, BLK), d_sa, n32, seen, bad);
+        CU_TRY(c, cudaMemsetAsync(tab + T_HIST, 0, 256 * 4, c->stream));
+        uint32_t hb = cdiv(n, BLK * 64);
+        if (hb > 1184) hb = 1184;
+        LAUNCH(c, k_byte_hist, hb, d_text, n, tab + T_HIST);
+        LAUNCH(c, k_alpha_from_hist, 1, tab + T_HIST, tab + T_CODE, tab + T_ALPHA, sm + 3);
+        TRY(read_words(c, sm, 16));
+        if (c->h_pin[12] != 0) {      // identical on every rank: all fail together
+            c->last_error = "table is not a permutation of 0..n-1 (index out of range or repeated)";
+            return B200SA_ERR_BAD_ARG;
+        }
+        TRY(pack_text(c, d_text, n, c->h_pin[3]));
+    }
+    // ---- Phi and PLCP of this rank's text range
+    TRY(mark(c, "lcps_plcp"));
+    const uint64_t lo = (uint64_t)R * per, hi = (lo + per < n) ? lo + per : (lo < n ? n : lo);
+    uint32_t *phi = ptr<uint32_t>(c->isa);
+    uint32_t nchunk = cdiv(n, LCP_CHUNK);
+    TRY(ensure(c, c->plcp_samp, (size_t)nchunk * 4));
+    uint32_t *samp = ptr<uint32_t>(c->plcp_samp);
+    if (hi > lo) {
+        LAUNCH(c, k_phi_range, cdiv(n, BLK), d_sa, n32, (uint32_t)lo, (uint32_t)hi, phi);
+        uint64_t len = hi - lo;
+        uint32_t chunks = cdiv(len, LCP_CHUNK);
+        uint32_t pg = cdiv(chunks, BLK), sg = cdiv(cdiv(chunks, 32), BLK);
+        uint64_t toff_s = lo / (32ull * LCP_CHUNK), toff_p = lo / LCP_CHUNK;
+        if (c->bits == 2) LAUNCH(c, (k_plcp_samples<2>), sg, c->ptext, n32, phi, samp, toff_s, hi);
+        else if (c->bits == 4) LAUNCH(c, (k_plcp_samples<4>), sg, c->ptext, n32, phi, samp, toff_s, hi);
+        else LAUNCH(c, (k_plcp_samples<8>), sg, c->ptext, n32, phi, samp, toff_s, hi);
+        if (c->bits == 2) LAUNCH(c, (k_plcp<2>), pg, c->ptext, n32, phi, samp, toff_p, hi);
+        else if (c->bits == 4) LAUNCH(c, (k_plcp<4>), pg, c->ptext, n32, phi, samp, toff_p, hi);
+        else LAUNCH(c, (k_plcp<8>), pg, c->ptext, n32, phi, samp, toff_p, hi);
+    }
+    TRY(mark(c, "lcps_allgather_plcp"));
+    if (W > 1) NCCL_TRY(c, N.AllGather(phi + lo, phi, per, ncclUint32, c->comm, c->stream));
+    // ---- LCP of this rank's RANK range, then the slices to everybody
+    TRY(mark(c, "lcps_gather"));
+    TRY(ensure(c, c->phik, (size_t)W * per * 4));
+    uint32_t *slices = ptr<uint32_t>(c->phik);
+    if (hi > lo) LAUNCH(c, k_lcp_gather_range, cdiv(hi - lo, BLK), d_sa, phi, (uint32_t)lo, (uint32_t)hi, slices + lo);
+    TRY(mark(c, "lcps_allgather_lcp"));
+    if (W > 1) NCCL_TRY(c, N.AllGather(slices + lo, slices, per, ncclUint32, c->comm, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(d_lcp, slices, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    TRY(mark(c, "end"));
+    CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return end_call(c);
 }

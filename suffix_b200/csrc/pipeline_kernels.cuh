@@ -374,15 +374,18 @@ constexpr int LCP_CHUNK = 32;
 // h = 0 happens once per 1024 positions instead of once per 32 (inside a run or
 // repeat of length L a restart costs O(L)).
 constexpr uint32_t LCP_SOLO = 256;       // chars a lane compares alone before the warp takes over
+// (t_off, pos_end): text-range sharding (multi-GPU LCP) -- threads start at sample group t_off and
+// positions at or beyond pos_end belong to another rank.
 template <int BITS>
 __global__ void __launch_bounds__(BLK) k_plcp_samples(const void *__restrict__ ptext, uint32_t n,
-                                                      const uint32_t *__restrict__ phi, uint32_t *samp) {
-    uint64_t t = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+                                                      const uint32_t *__restrict__ phi, uint32_t *samp,
+                                                      uint64_t t_off, uint64_t pos_end) {
+    uint64_t t = t_off + (uint64_t)blockIdx.x * BLK + threadIdx.x;
     uint64_t s0 = t * 32;
     uint32_t h = 0;
     for (int j = 0; j < 32; j++) {                       // no early exit: the warp cooperates below
         uint64_t sidx = s0 + j, i = sidx * LCP_CHUNK;
-        bool live = i < n;
+        bool live = i < n && i < pos_end;
         uint32_t jp = live ? phi[i] : PHI_NONE;
         bool cmp = live && jp != PHI_NONE;
         uint32_t a = 0, b = 0, limit = 0, got = 0;
@@ -414,10 +417,10 @@ __global__ void __launch_bounds__(BLK) k_plcp_samples(const void *__restrict__ p
 // on exit.
 template <int BITS>
 __global__ void __launch_bounds__(BLK) k_plcp(const void *__restrict__ ptext, uint32_t n, uint32_t *buf,
-                                              const uint32_t *__restrict__ samp) {
-    uint64_t t = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+                                              const uint32_t *__restrict__ samp, uint64_t t_off, uint64_t pos_end) {
+    uint64_t t = t_off + (uint64_t)blockIdx.x * BLK + threadIdx.x;
     uint64_t i0 = t * LCP_CHUNK;
-    if (i0 >= n) return;
+    if (i0 >= n || i0 >= pos_end) return;
     uint64_t i1 = i0 + LCP_CHUNK;
     if (i1 > n) i1 = n;
     uint32_t h = samp[t];
@@ -432,6 +435,20 @@ __global__ void __launch_bounds__(BLK) k_plcp(const void *__restrict__ ptext, ui
         buf[i] = h;
         if (h > 0) h--;
     }
+}
+// phi restricted to the text range [lo, hi) of one rank (the whole SA is scanned; the writes fall
+// into a range small enough to stay in L2)
+__global__ void __launch_bounds__(BLK) k_phi_range(const uint32_t *__restrict__ sa, uint32_t n, uint32_t lo, uint32_t hi,
+                                                   uint32_t *phi) {
+    uint32_t r = blockIdx.x * BLK + threadIdx.x;
+    if (r >= n) return;
+    uint32_t i = sa[r];
+    if (i >= lo && i < hi) phi[i] = r ? sa[r - 1] : PHI_NONE;
+}
+__global__ void __launch_bounds__(BLK) k_lcp_gather_range(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ plcp,
+                                                          uint32_t lo, uint32_t hi, uint32_t *out) {
+    uint32_t r = lo + blockIdx.x * BLK + threadIdx.x;
+    if (r < hi) out[r - lo] = plcp[sa[r]];
 }
 __global__ void __launch_bounds__(BLK) k_lcp_gather(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ plcp,
                                                     uint32_t n, uint32_t *lcp) {
@@ -489,6 +506,108 @@ __global__ void __launch_bounds__(BLK) k_positions(const uint8_t *__restrict__ t
     }
     out_start[qi] = start;
     out_end[qi] = end;
+}
+
+// ------------------------------------------------------------ generalized suffix array
+// document of a text position: doc_starts[d] <= pos < doc_starts[d+1] (ascending, doc_starts[ndocs] = n);
+// positions of separator bytes map to the document they terminate.
+__global__ void __launch_bounds__(BLK) k_doc_ids(const uint32_t *__restrict__ pos, uint64_t count,
+                                                 const uint32_t *__restrict__ doc_starts, uint32_t ndocs,
+                                                 uint32_t *doc, uint32_t *off) {
+    uint64_t i = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+    if (i >= count) return;
+    uint32_t p = pos[i], lo = 0, hi = ndocs;            // last d with doc_starts[d] <= p
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (__ldg(doc_starts + mid) <= p) lo = mid; else hi = mid;
+    }
+    doc[i] = lo;
+    off[i] = p - __ldg(doc_starts + lo);
+}
+
+// ------------------------------------------------------------ LCP-interval tree
+// The internal nodes of the suffix tree are the LCP intervals (reference builds the pointer tree
+// serially from SA + LCP, suffix_tree/src/lib.rs:392-505).  For every rank i: psv[i] = largest j < i
+// with lcp[j] < lcp[i] (NONE if none), nsv[i] = smallest j > i with lcp[j] < lcp[i] (n if none): the
+// node that owns boundary i is the interval [psv[i], nsv[i]) of string depth lcp[i].  Minima over
+// blocks of 32^k entries let every thread skip whole blocks.
+constexpr uint32_t ANSV_NONE = 0xffffffffu;
+__global__ void __launch_bounds__(BLK) k_min32(const uint32_t *__restrict__ in, uint64_t n_in, uint32_t *out) {
+    uint64_t b = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+    uint64_t i0 = b * 32;
+    if (i0 >= n_in) return;
+    uint32_t m = 0xffffffffu;
+    for (int k = 0; k < 32 && i0 + k < n_in; k++) { uint32_t v = in[i0 + k]; m = v < m ? v : m; }
+    out[b] = m;
+}
+struct AnsvLevels {
+    const uint32_t *lv[8];     // lv[0] = lcp, lv[k] = minima over 32^k entries
+    uint64_t cnt[8];
+    int nlev;
+};
+__device__ __forceinline__ uint32_t ansv_left(const AnsvLevels &L, uint64_t i, uint32_t v) {
+    // climb: at level k, scan the siblings to the left inside the parent block; a block with min < v holds the answer
+    uint64_t idx = i;
+    int k = 0;
+    while (true) {
+        uint64_t first = idx & ~(uint64_t)31;
+        uint64_t j = idx;
+        bool found = false;
+        while (j > first) {
+            j--;
+            if (L.lv[k][j] < v) { found = true; break; }
+        }
+        if (found) {                       // descend: rightmost entry < v inside block j of level k
+            while (k > 0) {
+                uint64_t base = j * 32, end = base + 32;
+                if (end > L.cnt[k - 1]) end = L.cnt[k - 1];
+                uint64_t q = end;
+                while (q > base) { q--; if (L.lv[k - 1][q] < v) break; }
+                j = q;
+                k--;
+            }
+            return (uint32_t)j;
+        }
+        if (k + 1 >= L.nlev || (idx >> 5) == 0) {
+            if (k + 1 >= L.nlev) return ANSV_NONE;
+        }
+        idx >>= 5;
+        k++;
+        if (k >= L.nlev) return ANSV_NONE;
+        if (idx == 0) return ANSV_NONE;
+    }
+}
+__device__ __forceinline__ uint64_t ansv_right(const AnsvLevels &L, uint64_t i, uint32_t v, uint64_t n) {
+    uint64_t idx = i;
+    int k = 0;
+    while (true) {
+        uint64_t last = (idx | 31) + 1;
+        if (last > L.cnt[k]) last = L.cnt[k];
+        uint64_t j = idx + 1;
+        bool found = false;
+        for (; j < last; j++) if (L.lv[k][j] < v) { found = true; break; }
+        if (found) {
+            while (k > 0) {
+                uint64_t base = j * 32, end = base + 32;
+                if (end > L.cnt[k - 1]) end = L.cnt[k - 1];
+                uint64_t q = base;
+                while (q < end && !(L.lv[k - 1][q] < v)) q++;
+                j = q;
+                k--;
+            }
+            return j;
+        }
+        idx >>= 5;
+        k++;
+        if (k >= L.nlev) return n;
+    }
+}
+__global__ void __launch_bounds__(BLK) k_ansv(AnsvLevels L, uint64_t n, uint32_t *psv, uint32_t *nsv) {
+    uint64_t i = (uint64_t)blockIdx.x * BLK + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = L.lv[0][i];
+    psv[i] = ansv_left(L, i, v);
+    nsv[i] = (uint32_t)ansv_right(L, i, v, n);
 }
 
 }  // namespace b200sa

@@ -141,6 +141,24 @@ class SuffixTable:
                 hi = mid
         return None
 
+    # ---- LCP-interval tree (the node set of the reference's suffix tree,
+    # suffix_tree/src/lib.rs:392-505): (psv, nsv) per rank from b200sa_lcp_intervals_dev
+    def lcp_intervals(self, lcp=None):
+        """Returns (lcp, psv, nsv): the internal node owning the boundary before rank i is the
+        interval [psv[i], nsv[i]) of string depth lcp[i] (psv == 0xFFFFFFFF: none to the left)."""
+        import torch
+        lcp = self.lcp_lens() if lcp is None else np.ascontiguousarray(lcp, dtype=np.uint32)
+        n = len(lcp)
+        dev = torch.device("cuda", self._device)
+        d_l = torch.from_numpy(lcp.astype(np.int64)).to(dev).to(torch.int32)
+        d_p = torch.empty(n, dtype=torch.int32, device=dev)
+        d_n = torch.empty(n, dtype=torch.int32, device=dev)
+        with _lock:
+            _lib.default_context(self._device).lcp_intervals_dev(d_l.data_ptr(), n, d_p.data_ptr(), d_n.data_ptr(),
+                                                                 torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return lcp, d_p.cpu().numpy().view(np.uint32), d_n.cpu().numpy().view(np.uint32)
+
     # ---- persistence (SURVEY 8f-2): the only "wire format" the reference API implies is
     # from_parts/into_parts (src/table.rs:111-127): text bytes + little-endian u32 table.
     def save(self, path: str) -> None:

@@ -274,3 +274,124 @@ def test_sharded_lms_sort_nccl_two_gpus():
         nm = np.concatenate([res[r][k][1] for r in range(2)])
         _check_global_order(t, g, nm, res[0][k][2], res[0][k][3])
         assert res[0][k][4] > 0 or res[1][k][4] > 0          # something crossed NVLink
+
+
+# ---------------------------------------------------------------------------------------
+# sharded LCP: text-range-sharded Phi / PLCP
+def _lcp_range_worker(rank, world, port, texts, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = []
+    for t in texts:
+        n = len(t)
+        objs = [None]
+        if rank == 0:
+            objs = [oracle.sais(t)]                        # rank 0 holds the table; broadcast like the product does
+        dist.broadcast_object_list(objs, src=0)
+        sa = objs[0]
+        per = ((n + world - 1) // world + 1023) // 1024 * 1024
+        lo, hi = min(n, rank * per), min(n, rank * per + per)
+        phi = {}
+        for r in range(n):                                  # Phi restricted to the rank's text range
+            i = int(sa[r])
+            if lo <= i < hi:
+                phi[i] = int(sa[r - 1]) if r else -1
+        plcp = np.zeros(max(hi - lo, 0), dtype=np.int64)
+        h = 0
+        for i in range(lo, hi):                             # PLCP with the h-1 carry, restart at the range start
+            j = phi[i]
+            if j < 0:
+                h = 0
+            else:
+                while i + h < n and j + h < n and t[i + h] == t[j + h]:
+                    h += 1
+            plcp[i - lo] = h
+            h = max(h - 1, 0)
+        parts = [None] * world
+        dist.all_gather_object(parts, plcp)
+        full = np.concatenate(parts)[:n]
+        lcp_slice = full[sa[lo:hi]]                         # this rank's RANK range
+        dist.all_gather_object(parts, lcp_slice)
+        out.append(np.concatenate(parts)[:n])
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_lcp_model_gloo(world):
+    texts = [gen.dna(5000), gen.rand_bytes(3000), np.frombuffer(b"abracadabra" * 200, dtype=np.uint8), gen.english(4000)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lcp_range_worker, args=(r, world, port, texts, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    for k, t in enumerate(texts):
+        want = oracle.lcp_kasai(t, oracle.sais(t)).astype(np.int64)
+        for r in range(world):
+            assert np.array_equal(res[r][k], want), (k, r)
+
+
+@pytest.mark.gpu
+def test_sharded_lcp_cuda_world1():
+    from suffix_b200 import _lib
+    ctx = _lib.Context(0)
+    for t in (gen.dna(2_000_000), gen.rand_bytes(700_001), gen.fixture("AP009048_100000.fasta"), gen.english(300_000)):
+        sa = oracle.sais(t)
+        d_t = torch.from_numpy(t.copy()).cuda()
+        d_sa = torch.from_numpy(sa.astype(np.int64)).cuda().to(torch.int32)
+        d_lcp = torch.empty(len(t), dtype=torch.int32, device="cuda")
+        ctx.lcp_sharded(d_t.data_ptr(), len(t), d_sa.data_ptr(), d_lcp.data_ptr(), False,
+                        torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_lcp.cpu().numpy().view(np.uint32), oracle.lcp_kasai(t, sa))
+    ctx.close()
+
+
+def _nccl_lcp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from suffix_b200 import _lib
+    ctx = _lib.Context(rank)
+    sharded.ensure_comm(ctx, dist)
+    ok = True
+    for t in (gen.dna(3_000_000), gen.rand_bytes(1_000_001)):
+        n = len(t)
+        sa = oracle.sais(t)
+        dev = torch.device("cuda", rank)
+        if rank == 0:                                       # only rank 0 holds text and table
+            d_t = torch.from_numpy(t.copy()).to(dev)
+            d_sa = torch.from_numpy(sa.astype(np.int64)).to(dev).to(torch.int32)
+        else:
+            d_t = torch.zeros(n, dtype=torch.uint8, device=dev)
+            d_sa = torch.zeros(n, dtype=torch.int32, device=dev)
+        d_lcp = torch.empty(n, dtype=torch.int32, device=dev)
+        ctx.lcp_sharded(d_t.data_ptr(), n, d_sa.data_ptr(), d_lcp.data_ptr(), False, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ok = ok and bool(np.array_equal(d_lcp.cpu().numpy().view(np.uint32), oracle.lcp_kasai(t, sa)))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_lcp_nccl_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_lcp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m "gpu and not slow" -q --tb=short -x > gpurun_out/gpu_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests.log; tail -4 gpurun_out/gpu_tests.log
-timeout 200 python tools/phase_times.py 100000000 --kinds=dna,dna_nl,bytes 2>&1 | tee gpurun_out/phase100.log | cut -c1-900
+timeout 900 python -m pytest tests/test_gpu_next.py tests/test_sharded.py -m "gpu" -q --tb=short -x 2>&1 | tail -15
+timeout 300 python tools/positions_bench.py 100000000 1000000 2>&1 | tail -2 | tee gpurun_out/positions_bench.json
