@@ -23,6 +23,7 @@
 #include "induce2.cuh"
 #include "induce3.cuh"
 #include "induce4.cuh"
+#include "induce5.cuh"
 #include "pipeline_kernels.cuh"
 #include "lms_sort.cuh"
 #include "shard.cuh"
@@ -46,7 +47,7 @@ struct b200sa_ctx {
     int induce_blocks = 0;          // largest co-resident grid (workspace is sized for it)
     int induce_bps_max = 1;         // occupancy bound over all variants, blocks per SM
     int induce_occ[3] = {1, 1, 1};  // occupancy bound per text packing (2, 4, 8 bits) of the default variant
-    int induce_occ_v[5][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}};   // per kernel variant
+    int induce_occ_v[6][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}};   // per kernel variant
     int induce_bps_env = 0;         // B200SA_INDUCE_BPS override (0 = adaptive)
     int cur_induce_blocks = 0;      // grid of the current build
     std::string last_error;
@@ -614,7 +615,8 @@ static int lms_direct_sort(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **lis
 // Kernel variants of the induce passes: 1 = one-round steps with MATCH ranking (any packing),
 // 2 = multi-round bucket steps (packed text), 3 = packed-counter ranking (2-bit text only),
 // 4 = 3 + carried predecessor chars + staged coalesced stores (2-bit text only).  Default for 2-bit
-// text: 3.  B200SA_INDUCE=1|2|3|4 forces a variant (profiles/README.md has the comparison).
+// 5 = warp-private tile streams + 16-bit carried chars with producer-side refresh + staged stores
+// (2-bit text).  Default for 2-bit text: 3.  B200SA_INDUCE=1|2|3|4|5 forces a variant (profiles/README.md compares them).
 static int induce_variant_env() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("B200SA_INDUCE"); v = e ? atoi(e) : 0; }
@@ -624,10 +626,11 @@ static int induce_variant(int bits) {
     int v = induce_variant_env();
     if (v == 2 && bits < 8) return 2;
     if (v == 1) return 1;
-    if (bits == 2) return v == 4 ? 4 : 3;      // measured on 100 MB DNA: 3 and 4 within 4 % of each other; 3 moves fewer bytes
+    if (bits == 2) return (v == 4 || v == 5) ? v : 3;      // measured (profiles/README.md): 3 is the fastest on 100 MB DNA
     return 1;
 }
 static const void *induce_fn_v(bool spass, int bits, int variant) {
+    if (variant == 5 && bits == 2) return spass ? (const void *)k_induce5<true> : (const void *)k_induce5<false>;
     if (variant == 4 && bits == 2) return spass ? (const void *)k_induce4<true> : (const void *)k_induce4<false>;
     if (variant == 3 && bits == 2) return spass ? (const void *)k_induce3<true> : (const void *)k_induce3<false>;
     if (variant == 2 && bits == 2) return spass ? (const void *)k_induce2<true, 2> : (const void *)k_induce2<false, 2>;
@@ -662,7 +665,7 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
     void *args[] = {&A};
     int variant = induce_variant(c->bits);
     if (variant >= 3 && (((uintptr_t)sa | (uintptr_t)lms) & 15) != 0) variant = 1;      // 16-byte loads need aligned arrays
-    A.carry = (variant == 4) ? 1 : 0;
+    A.carry = (variant == 5) ? 2 : (variant == 4 ? 1 : 0);
     int bi = c->bits == 2 ? 0 : (c->bits == 4 ? 1 : 2);
     int blocks = c->cur_induce_blocks, cap = c->sm_count * c->induce_occ_v[variant][bi];
     if (blocks > cap) blocks = cap;
@@ -838,9 +841,9 @@ static int build_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, uint32_t 
     }
     c->stats.m = m; c->last_m = m;
     c->stats.induce_blocks = c->cur_induce_blocks;
-    TRY(ensure(c, c->pred, n));
+    TRY(ensure(c, c->pred, 2 * n + 64));          // bytes (variants 1-4) or 16-bit carried words (variant 5)
     TRY(ensure(c, c->lmslist, (size_t)m * 4));
-    TRY(ensure(c, c->lmspred, m));
+    TRY(ensure(c, c->lmspred, 2 * (size_t)m + 64));
     TRY(ensure(c, c->blkcnt, (size_t)2 * c->induce_blocks * 256 * 4));
     TRY(ensure(c, c->runscr, (size_t)2 * TILE * 4));
     uint32_t *lmslist = ptr<uint32_t>(c->lmslist);
@@ -1131,7 +1134,7 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
     int occ = 0;
     {
         const int bb[3] = {2, 4, 8};
-        for (int v = 1; v <= 4; v++)
+        for (int v = 1; v <= 5; v++)
             for (int k = 0; k < 3; k++) {
                 int ok = 1 << 30;
                 for (int sp = 0; sp < 2; sp++) {
@@ -1143,7 +1146,7 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
             }
         for (int k = 0; k < 3; k++) {
             c->induce_occ[k] = c->induce_occ_v[induce_variant(bb[k])][k];
-            for (int v = 1; v <= 4; v++) if (c->induce_occ_v[v][k] > occ) occ = c->induce_occ_v[v][k];
+            for (int v = 1; v <= 5; v++) if (c->induce_occ_v[v][k] > occ) occ = c->induce_occ_v[v][k];
         }
     }
     if (occ < 1) { cudaFreeHost(c->h_pin); delete c; return B200SA_ERR_CUDA; }

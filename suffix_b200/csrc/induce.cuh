@@ -45,7 +45,8 @@ struct InduceArgs {
     uint32_t *run_scratch;   // [TILE] run-skipping: terminal entries in scan order
     uint32_t *run_alive;     // [TILE] run-skipping: alive entries of the epoch being emitted grid-wide
     uint32_t *cmd;           // [8]    block 0 -> grid: {cmd, a, t_prev, rounds, base pos, bucket}
-    int carry;               // k_induce4: pred[] carries predecessor chars per SA slot; products of the shared small-step code mark theirs "unknown" (0)
+    int carry;               // 1: pred[] carries predecessor chars per SA slot as bytes (k_induce4), 2: as 16-bit words
+                             // (k_induce5); products of the shared small-step code mark theirs "unknown" (0)
     unsigned long long *steplog;   // diagnostics (B200SA_STEPLOG): [0] = count, then (globaltimer ns, list length) pairs
 };
 enum { CMD_NONE = 0, CMD_EMIT = 1, CMD_DONE = 2 };
@@ -162,7 +163,7 @@ __device__ __forceinline__ void tile_scatter(const InduceArgs &A, IndShared &sh,
             uint32_t pos = sh.base[d[r]] + sh.wcnt[w][d[r]] + rank[r];
             uint32_t slot = SPASS ? (sh.bstart[d[r] + 1] - 1u - pos) : (sh.bstart[d[r]] + pos);
             A.sa[slot] = s[r] - 1u;
-            if (A.carry) A.pred[slot] = 0;
+            if (A.carry == 1) A.pred[slot] = 0; else if (A.carry == 2) reinterpret_cast<uint16_t *>(A.pred)[slot] = 0;
         }
     }
     __syncthreads();
@@ -276,7 +277,7 @@ __device__ __forceinline__ void grid_emit(const InduceArgs &A, const IndShared &
         uint32_t pos = basepos + (uint32_t)idx;
         uint32_t slot = SPASS ? (sh.bstart[c + 1] - 1u - pos) : (sh.bstart[c] + pos);
         A.sa[slot] = __ldcg(A.run_alive + jj) - (t_prev + 1u + r_off);
-        if (A.carry) A.pred[slot] = 0;
+        if (A.carry == 1) A.pred[slot] = 0; else if (A.carry == 2) reinterpret_cast<uint16_t *>(A.pred)[slot] = 0;
     }
 }
 
@@ -366,7 +367,7 @@ __device__ __noinline__ void induce_run_skip(const InduceArgs &A, IndShared &sh,
                     uint32_t pos = F + (uint32_t)(O + idx);
                     uint32_t slot = SPASS ? (sh.bstart[c + 1] - 1u - pos) : (sh.bstart[c] + pos);
                     A.sa[slot] = sh.alive[jj] - (t_prev + 1u + r_off);
-                    if (A.carry) A.pred[slot] = 0;
+                    if (A.carry == 1) A.pred[slot] = 0; else if (A.carry == 2) reinterpret_cast<uint16_t *>(A.pred)[slot] = 0;
                 }
             }
             O += items;

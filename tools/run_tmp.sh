@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_next.py tests/test_sharded.py -m "gpu" -q --tb=short -x 2>&1 | tail -15
-timeout 300 python tools/positions_bench.py 100000000 1000000 2>&1 | tail -2 | tee gpurun_out/positions_bench.json
+timeout 600 python -m pytest tests -m "gpu and not slow" -q --tb=short -x > gpurun_out/gpu_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests.log; tail -8 gpurun_out/gpu_tests.log
+echo "== default (v5/16-bit)"; timeout 200 python tools/phase_times.py 100000000 --kinds=dna 2>&1 | cut -c1-600
+timeout 120 python tools/steplog.py 100000000 > gpurun_out/steplog_dna_v5.txt 2>&1; head -30 gpurun_out/steplog_dna_v5.txt
