@@ -85,6 +85,7 @@ template <int BITS>
 struct LmsKeyDesc {
     LmsWin W; const uint32_t *lmsdesc;
     __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return lms_window<BITS>(W, __ldg(lmsdesc + i)); }
+    __device__ __forceinline__ uint32_t at(uint64_t, uint32_t pos) const { return lms_window<BITS>(W, pos); }   // value = position
 };
 struct LmsValDesc {
     const uint32_t *lmsdesc;
