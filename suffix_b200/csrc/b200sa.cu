@@ -656,6 +656,7 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
     A.cmd = sm + 336;
     A.steplog = nullptr;
     A.carry = 0;
+    { static int rs = -1; if (rs < 0) { const char *e = getenv("B200SA_RUN_STREAK"); rs = e ? atoi(e) : 0; } A.run_streak = (uint32_t)rs; }
     if (getenv("B200SA_STEPLOG")) {
         if (ensure(c, c->steplog, 4096 * 8) == B200SA_OK) {
             A.steplog = ptr<unsigned long long>(c->steplog);

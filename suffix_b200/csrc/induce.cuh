@@ -47,6 +47,7 @@ struct InduceArgs {
     uint32_t *cmd;           // [8]    block 0 -> grid: {cmd, a, t_prev, rounds, base pos, bucket}
     int carry;               // 1: pred[] carries predecessor chars per SA slot as bytes (k_induce4), 2: as 16-bit words
                              // (k_induce5); products of the shared small-step code mark theirs "unknown" (0)
+    uint32_t run_streak;     // small chain rounds in one bucket before the chain is finished at once (0: RUN_STREAK)
     unsigned long long *steplog;   // diagnostics (B200SA_STEPLOG): [0] = count, then (globaltimer ns, list length) pairs
 };
 enum { CMD_NONE = 0, CMD_EMIT = 1, CMD_DONE = 2 };
@@ -430,7 +431,7 @@ __device__ __noinline__ void induce_small_episode(const InduceArgs &A, IndShared
                 else { sh.streak = chain ? 1u : 0u; sh.streak_c = chain ? cc : -1; }
             }
             __syncthreads();
-            if (chain && sh.streak >= RUN_STREAK) {
+            if (chain && sh.streak >= (A.run_streak ? A.run_streak : RUN_STREAK)) {
                 induce_run_skip<SPASS, BITS>(A, sh, g, (uint32_t)cc, grid);
                 if (tid == 0) { sh.st_c = cc; sh.st_phase = 0; sh.st_begin = sh.fill[cc]; sh.streak = 0; sh.streak_c = -1; }
                 __syncthreads();
