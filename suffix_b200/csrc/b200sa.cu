@@ -24,6 +24,7 @@
 #include "induce3.cuh"
 #include "induce4.cuh"
 #include "induce5.cuh"
+#include "induce6.cuh"
 #include "pipeline_kernels.cuh"
 #include "lms_sort.cuh"
 #include "shard.cuh"
@@ -47,7 +48,7 @@ struct b200sa_ctx {
     int induce_blocks = 0;          // largest co-resident grid (workspace is sized for it)
     int induce_bps_max = 1;         // occupancy bound over all variants, blocks per SM
     int induce_occ[3] = {1, 1, 1};  // occupancy bound per text packing (2, 4, 8 bits) of the default variant
-    int induce_occ_v[6][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}};   // per kernel variant
+    int induce_occ_v[7][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}};   // per kernel variant
     int induce_bps_env = 0;         // B200SA_INDUCE_BPS override (0 = adaptive)
     int cur_induce_blocks = 0;      // grid of the current build
     std::string last_error;
@@ -548,15 +549,17 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
     uint32_t na = c->h_pin[0];
     c->stats.names = m - na;                       // LMS suffixes settled by the first window
     uint32_t rounds = 1;
-    uint32_t max_rounds = 6;
+    uint32_t max_rounds = BITS == 8 ? 16u : 8u;    // byte windows hold 4-8 chars: natural text needs ~10 of them
     if (const char *e = getenv("B200SA_DIRECT_ROUNDS")) { int v = atoi(e); if (v >= 1) max_rounds = (uint32_t)v; }
     if (getenv("B200SA_TRACE")) fprintf(stderr, "[b200sa] direct LMS sort: kc=%u, round 1 leaves %u of %u tied\n", kc, na, m);
     const bool force = getenv("B200SA_DIRECT_FORCE") != nullptr;            // experiments: never bail out early
-    if (!force && (uint64_t)na * 10 > (uint64_t)m * 9 && m > 64) return B200SA_OK;   // the window tells nothing apart
+    // the window tells (almost) nothing apart: every suffix has a twin for kc characters -- repeats, not
+    // a skewed alphabet (English leaves 99.5 % tied after 5 bytes and still converges in ~10 rounds)
+    if (!force && (uint64_t)na * 1000 > (uint64_t)m * 999 && m > 64) return B200SA_OK;
     if (na > 0)     // group id of every tied element = slot of its group's head
         TRY((dev_scan<OpMax>(c, InArray{grpA}, OutMaxInPlace{grpA}, na, nullptr)));
     uint64_t h = kc;
-    bool try_local = getenv("B200SA_NO_LOCAL_SORT") == nullptr;
+    const bool allow_local = getenv("B200SA_NO_LOCAL_SORT") == nullptr;
     const int gbits = 32 + bit_length(m);
     while (na > 0) {
         if (rounds >= max_rounds) return B200SA_OK;            // still tied: robust path
@@ -573,14 +576,22 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
         LAUNCH(c, (k_lms_refine_keys<BITS>), cdiv(na, BLK), W, posA, grpA, na, (uint32_t)h, KA);
         const uint32_t span = (uint32_t)(h + kc > 0xffffffffull ? 0xffffffffull : h + kc);
         bool local_ok = false;
+        bool try_local = allow_local;
+        if (try_local) {                        // probe ~4096 elements: counting inside a group is quadratic in its size
+            CU_TRY(c, cudaMemsetAsync(sm + 24, 0, 16, c->stream));   // [24] overflow, [25] members of big groups, [26] max size
+            uint32_t stride = na / 4096u; if (stride < 1) stride = 1;
+            uint32_t samples = cdiv(na, stride);
+            LAUNCH(c, k_group_probe, cdiv(samples, BLK), KA, na, 32u, stride, sm + 25);
+            TRY(read_words(c, sm + 25, 2));
+            if (c->h_pin[0] * 20u > samples) try_local = false;     // > 5 % of the elements sit in groups of >= 128
+        }
         if (try_local) {                         // tiny groups: rank inside the group by counting
             CU_TRY(c, cudaMemsetAsync(sm + 24, 0, 4, c->stream));
             LAUNCH(c, k_group_local_sort, cdiv(na, BLK), KA, posA, na, 32u, KB, scratch, sm + 24);
             TRY((dev_scan<OpMaxSum>(c, InLmsGroupR{KB, scratch, slotA, na, n, span},
                                     OutLmsCompactR{scratch, slotA, Ps, slotB, posB, grpB}, na, d_tot)));
             TRY(read_words(c, sm + 16, 9));          // [0] tied count ... [8] = sm[24] overflow flag
-            local_ok = c->h_pin[8] == 0;
-            if (!local_ok) try_local = false;        // some group is large: radix sort from now on
+            local_ok = c->h_pin[8] == 0;             // some group larger than the limit: radix sort this round
         }
         if (!local_ok) {
             TRY(sort_pairs<uint64_t>(c, KA, posA, KB, scratch, na, gbits, &K2, &P2));
@@ -592,7 +603,7 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
         uint32_t na_next = c->h_pin[0];
         if (getenv("B200SA_TRACE")) fprintf(stderr, "[b200sa] direct LMS sort: round %u (h=%llu): %u -> %u tied\n", rounds, (unsigned long long)h, na, na_next);
         // slow convergence on a large residue means long repeats: stop early
-        if (!force && rounds >= 3 && (uint64_t)na_next * 2 > na && (uint64_t)na_next * 64 > m) return B200SA_OK;
+        if (!force && (uint64_t)na_next * 100 > (uint64_t)na * 85 && (uint64_t)na_next * 64 > m) return B200SA_OK;
         na = na_next;
         uint32_t *t;
         t = slotA; slotA = slotB; slotB = t;
@@ -616,7 +627,7 @@ static int lms_direct_sort(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **lis
 // 2 = multi-round bucket steps (packed text), 3 = packed-counter ranking (2-bit text only),
 // 4 = 3 + carried predecessor chars + staged coalesced stores (2-bit text only).  Default for 2-bit
 // 5 = warp-private tile streams + 16-bit carried chars with producer-side refresh + staged stores
-// (2-bit text).  Default for 2-bit text: 3.  B200SA_INDUCE=1|2|3|4|5 forces a variant (profiles/README.md compares them).
+// (2-bit text), 6 = 3's block-wide tiles + 5's 16-bit carried chars (2-bit text; default there).  B200SA_INDUCE=1|2|3|4|5 forces a variant (profiles/README.md compares them).
 static int induce_variant_env() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("B200SA_INDUCE"); v = e ? atoi(e) : 0; }
@@ -626,10 +637,11 @@ static int induce_variant(int bits) {
     int v = induce_variant_env();
     if (v == 2 && bits < 8) return 2;
     if (v == 1) return 1;
-    if (bits == 2) return (v == 4 || v == 5) ? v : 3;      // measured (profiles/README.md): 3 is the fastest on 100 MB DNA
+    if (bits == 2) return (v >= 3 && v <= 5) ? v : 6;
     return 1;
 }
 static const void *induce_fn_v(bool spass, int bits, int variant) {
+    if (variant == 6 && bits == 2) return spass ? (const void *)k_induce6<true> : (const void *)k_induce6<false>;
     if (variant == 5 && bits == 2) return spass ? (const void *)k_induce5<true> : (const void *)k_induce5<false>;
     if (variant == 4 && bits == 2) return spass ? (const void *)k_induce4<true> : (const void *)k_induce4<false>;
     if (variant == 3 && bits == 2) return spass ? (const void *)k_induce3<true> : (const void *)k_induce3<false>;
@@ -666,7 +678,7 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
     void *args[] = {&A};
     int variant = induce_variant(c->bits);
     if (variant >= 3 && (((uintptr_t)sa | (uintptr_t)lms) & 15) != 0) variant = 1;      // 16-byte loads need aligned arrays
-    A.carry = (variant == 5) ? 2 : (variant == 4 ? 1 : 0);
+    A.carry = (variant >= 5) ? 2 : (variant == 4 ? 1 : 0);
     int bi = c->bits == 2 ? 0 : (c->bits == 4 ? 1 : 2);
     int blocks = c->cur_induce_blocks, cap = c->sm_count * c->induce_occ_v[variant][bi];
     if (blocks > cap) blocks = cap;
@@ -1135,7 +1147,7 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
     int occ = 0;
     {
         const int bb[3] = {2, 4, 8};
-        for (int v = 1; v <= 5; v++)
+        for (int v = 1; v <= 6; v++)
             for (int k = 0; k < 3; k++) {
                 int ok = 1 << 30;
                 for (int sp = 0; sp < 2; sp++) {
@@ -1147,7 +1159,7 @@ int b200sa_ctx_create(int device, b200sa_ctx **out) {
             }
         for (int k = 0; k < 3; k++) {
             c->induce_occ[k] = c->induce_occ_v[induce_variant(bb[k])][k];
-            for (int v = 1; v <= 5; v++) if (c->induce_occ_v[v][k] > occ) occ = c->induce_occ_v[v][k];
+            for (int v = 1; v <= 6; v++) if (c->induce_occ_v[v][k] > occ) occ = c->induce_occ_v[v][k];
         }
     }
     if (occ < 1) { cudaFreeHost(c->h_pin); delete c; return B200SA_ERR_CUDA; }

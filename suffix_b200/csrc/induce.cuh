@@ -541,12 +541,29 @@ __global__ void __launch_bounds__(BLK, INDUCE_MINB) k_induce(InduceArgs A) {
         grid.sync();
         // phase B: offsets, scatter
         {
-            uint32_t base = sh.fill[tid], tot = 0;
-            for (uint32_t b = 0; b < nact; b++) {
-                uint32_t v = __ldcg(cntbuf + (size_t)b * 256u + tid);
-                if (b < bid) base += v;
-                tot += v;
+            // column sums of the nact x 256 count matrix: rows are dealt to the warps and every lane
+            // reads 8 columns of a row with two 16-byte loads, so the whole matrix is in flight at once
+            // (one thread per column walking nact rows cost ~nact/4 L2 round trips per step: the largest
+            // fixed cost of the ~1000 steps of a sigma = 256 pass)
+            uint32_t bacc[8], tacc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { bacc[j] = 0; tacc[j] = 0; }
+            const uint32_t wq = warp_id(), lq = lane_id();
+#pragma unroll 4
+            for (uint32_t b = wq; b < nact; b += NWARP) {
+                const uint4 *row = reinterpret_cast<const uint4 *>(cntbuf + (size_t)b * 256u) + 2u * lq;
+                uint4 x = __ldcg(row), y = __ldcg(row + 1);
+                uint32_t v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+                const bool before = b < bid;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { tacc[j] += v[j]; bacc[j] += before ? v[j] : 0u; }
             }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { sh.wcnt[wq][8u * lq + j] = tacc[j]; sh.ent[wq * 256u + 8u * lq + j] = bacc[j]; }
+            __syncthreads();
+            uint32_t base = sh.fill[tid], tot = 0;
+#pragma unroll
+            for (int ww = 0; ww < NWARP; ww++) { tot += sh.wcnt[ww][tid]; base += sh.ent[ww * 256u + tid]; }
             sh.base[tid] = base;
             __syncthreads();
             if (tb0 < tb1) {

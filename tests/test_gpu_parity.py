@@ -279,6 +279,8 @@ def test_direct_path_taken(ctx):
     assert ctx.stats()["direct_sort"] == 1
     ctx.build(gen.dna(2_000_001, newline_tail=True))
     assert ctx.stats()["direct_sort"] == 1
+    ctx.build(gen.english(2_000_000))                  # 4-5 byte windows, ~10 rounds
+    assert ctx.stats()["direct_sort"] == 1
     ctx.build(gen.tiled(gen.fixture("AP009048_10000.fasta"), 2_000_000))
     assert ctx.stats()["direct_sort"] == 0
 
