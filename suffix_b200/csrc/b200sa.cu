@@ -210,6 +210,24 @@ static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, typename Op::T 
     return B200SA_OK;
 }
 
+// Scan descriptors for a kernel that embeds tile_lookback (same buffer and epochs as dev_scan).
+static int scan_state_for(b200sa_ctx *c, uint32_t nb, ScanState *S) {
+    size_t need = (size_t)nb * 20 + 64;
+    if (c->scan_state.cap < need) {
+        TRY(ensure(c, c->scan_state, need * 2));
+        CU_TRY(c, cudaMemsetAsync(c->scan_state.p, 0, c->scan_state.cap, c->stream));
+        c->scan_tiles_cap = (uint32_t)((c->scan_state.cap - 64) / 20);
+    }
+    uint8_t *basep = ptr<uint8_t>(c->scan_state);
+    S->ticket = reinterpret_cast<uint32_t *>(basep);
+    S->agg = reinterpret_cast<unsigned long long *>(basep + 64);
+    S->incl = S->agg + c->scan_tiles_cap;
+    S->flag = reinterpret_cast<uint32_t *>(S->incl + c->scan_tiles_cap);
+    c->scan_epoch += 2;
+    S->epoch = c->scan_epoch;
+    return B200SA_OK;
+}
+
 constexpr uint32_t MAX_RADIX_BLOCKS = 1184;   // 148 SMs x 8
 
 template <class DigF, class MoveF>
@@ -542,8 +560,16 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
         CU_TRY(c, cudaMemsetAsync(forced, 0, fw * 4, c->stream));
         CU_TRY(c, cudaMemsetAsync(sm + 16, 0, 8, c->stream));
         LAUNCH(c, (k_lms_mark_trunc<BITS>), 1u, W, ptr<uint32_t>(c->lmsdesc), m, Ks, Ps, kc, forced);
-        InLmsActive1 in1{Ks, forced, m};
-        TRY((dev_scan<OpSum>(c, in1, OutLmsCompact1{in1, Ps, slotA, posA, grpA}, m, sm + 16)));
+        if (getenv("B200SA_GROUPS_GENERIC")) {       // the generic scan with functors (cross-check)
+            InLmsActive1 in1{Ks, forced, m};
+            TRY((dev_scan<OpSum>(c, in1, OutLmsCompact1{in1, Ps, slotA, posA, grpA}, m, sm + 16)));
+        } else {
+            uint32_t nt = cdiv(m, LG_TILE);
+            ScanState S;
+            TRY(scan_state_for(c, nt, &S));
+            LAUNCH(c, k_lms_groups1, nt, Ks, Ps, forced, m, nt, S, slotA, posA, grpA, sm + 16);
+            CU_TRY(c, cudaGetLastError());
+        }
     }
     TRY(read_words(c, sm + 16, 1));
     uint32_t na = c->h_pin[0];
@@ -698,24 +724,6 @@ static int post_classify(b200sa_ctx *c, const uint8_t *text, uint64_t n, uint32_
     if (bps > occ_here) bps = occ_here;
     if (bps < 1) bps = 1;
     c->cur_induce_blocks = c->sm_count * bps;
-    return B200SA_OK;
-}
-
-// Scan descriptors for a kernel that embeds tile_lookback (same buffer and epochs as dev_scan).
-static int scan_state_for(b200sa_ctx *c, uint32_t nb, ScanState *S) {
-    size_t need = (size_t)nb * 20 + 64;
-    if (c->scan_state.cap < need) {
-        TRY(ensure(c, c->scan_state, need * 2));
-        CU_TRY(c, cudaMemsetAsync(c->scan_state.p, 0, c->scan_state.cap, c->stream));
-        c->scan_tiles_cap = (uint32_t)((c->scan_state.cap - 64) / 20);
-    }
-    uint8_t *basep = ptr<uint8_t>(c->scan_state);
-    S->ticket = reinterpret_cast<uint32_t *>(basep);
-    S->agg = reinterpret_cast<unsigned long long *>(basep + 64);
-    S->incl = S->agg + c->scan_tiles_cap;
-    S->flag = reinterpret_cast<uint32_t *>(S->incl + c->scan_tiles_cap);
-    c->scan_epoch += 2;
-    S->epoch = c->scan_epoch;
     return B200SA_OK;
 }
 

@@ -156,10 +156,8 @@ __global__ void __launch_bounds__(BLK) k_classify_fused(const uint8_t *__restric
             s_lms[k++] = (uint32_t)(w * 32 + j);
         }
     }
-    if (wp == 0) {
-        uint32_t prefix = tile_lookback<OpSum>(S, tile, btot, tile + 1 == ntiles, d_m);
-        if (l == 0) s_prefix = prefix;
-    }
+    if (tid == 0) tile_publish<OpSum>(S, tile, btot);       // the walk follows the histogram: by then the
+                                                            // predecessors have published inclusive prefixes
     // ---- histogram: warp-uniform candidate bytes first (small alphabets finish here)
     {
         uint32_t mM = lw, mS = sw & ~lw, mL = ~sw & vmask, todo = vmask;
@@ -182,6 +180,10 @@ __global__ void __launch_bounds__(BLK) k_classify_fused(const uint8_t *__restric
             uint32_t cls = ((sw >> j) & 1u) + ((lw >> j) & 1u);
             atomicAdd(&h[((c[j >> 2] >> ((j & 3) * 8)) & 0xffu) + 256u * cls], 1u);
         }
+    }
+    if (wp == 0) {
+        uint32_t prefix = tile_walk<OpSum>(S, tile, btot, tile + 1 == ntiles, d_m);
+        if (l == 0) s_prefix = prefix;
     }
     __syncthreads();
     // 12 k tiles adding to the same few global words serialise in L2 (measured: 47 % of this

@@ -219,21 +219,27 @@ struct ScanState {
     uint32_t epoch;
 };
 
-// Warp-0 part of a tile: publishes the tile aggregate, walks back over the predecessors and
-// publishes the inclusive prefix.  All 32 lanes of ONE warp call it; returns the exclusive
-// prefix of the tile (in every lane).  `last` = this is the final tile (writes *d_total).
+// Warp-0 part of a tile, in two halves so that a kernel can put independent work between them
+// (the walk is short once the predecessors had time to publish inclusive prefixes):
+//   tile_publish  -- one lane publishes the tile aggregate;
+//   tile_walk     -- all 32 lanes of ONE warp walk back over the predecessors (32 at a time) until an
+//                    inclusive prefix, publish this tile's inclusive prefix and return the exclusive one
+//                    (in every lane).  `last` = this is the final tile (writes *d_total).
 template <class Op>
-__device__ __forceinline__ typename Op::T tile_lookback(const ScanState &S, uint32_t tile, typename Op::T block_total,
-                                                        bool last, typename Op::T *d_total) {
+__device__ __forceinline__ void tile_publish(const ScanState &S, uint32_t tile, typename Op::T block_total) {
+    if (tile > 0) {
+        st_relaxed_u64(S.agg + tile, (unsigned long long)block_total);
+        __threadfence();
+        st_relaxed_u32(S.flag + tile, S.epoch + 1u);
+    }
+}
+template <class Op>
+__device__ __forceinline__ typename Op::T tile_walk(const ScanState &S, uint32_t tile, typename Op::T block_total,
+                                                    bool last, typename Op::T *d_total) {
     typedef typename Op::T T;
     const uint32_t l = lane_id();
     T prefix = Op::id();
     if (tile > 0) {
-        if (l == 0) {
-            st_relaxed_u64(S.agg + tile, (unsigned long long)block_total);
-            __threadfence();
-            st_relaxed_u32(S.flag + tile, S.epoch + 1u);
-        }
         int64_t t0 = (int64_t)tile - 1;
         while (true) {
             int64_t tt = t0 - (int64_t)l;            // lane 0: nearest predecessor
@@ -264,6 +270,12 @@ __device__ __forceinline__ typename Op::T tile_lookback(const ScanState &S, uint
         if (last && d_total) *d_total = total;
     }
     return prefix;
+}
+template <class Op>
+__device__ __forceinline__ typename Op::T tile_lookback(const ScanState &S, uint32_t tile, typename Op::T block_total,
+                                                        bool last, typename Op::T *d_total) {
+    if (lane_id() == 0) tile_publish<Op>(S, tile, block_total);
+    return tile_walk<Op>(S, tile, block_total, last, d_total);
 }
 
 template <class Op, class InF, class OutF>

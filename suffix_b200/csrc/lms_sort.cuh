@@ -144,6 +144,77 @@ struct OutLmsCompact1 {
         if (v) { aslot[exc] = (uint32_t)i; apos[exc] = P[i]; ahead[exc] = in.head((uint32_t)i) ? (uint32_t)i : 0u; }
     }
 };
+// The same compaction as ONE specialised single-pass kernel (the generic scan spends ~90
+// instructions per element on functor calls and 16 warp scans per thread; here a thread owns 16
+// consecutive slots, reads its 18 keys with four 16-byte loads + 2, derives heads / tied flags in
+// registers and takes part in one block scan; tile offsets by the same look-back as k_scan_lb).
+constexpr int LG_IPT = 16;
+constexpr int LG_TILE = BLK * LG_IPT;       // 4096 slots per tile
+__global__ void __launch_bounds__(BLK) k_lms_groups1(const uint32_t *__restrict__ K, const uint32_t *__restrict__ P,
+                                                     const uint32_t *__restrict__ forced, uint32_t m, uint32_t ntiles,
+                                                     ScanState S, uint32_t *aslot, uint32_t *apos, uint32_t *ahead,
+                                                     uint32_t *d_total) {
+    __shared__ uint32_t s_w[NWARP + 1];
+    __shared__ uint32_t s_tile, s_prefix;
+    if (threadIdx.x == 0) {
+        uint32_t t = atomicAdd(S.ticket, 1u);
+        if (t + 1 == ntiles) *S.ticket = 0u;
+        s_tile = t;
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t i0 = tile * LG_TILE + threadIdx.x * LG_IPT;
+    uint32_t k[LG_IPT + 2];                      // k[j+1] = K[i0 + j]; k[0] = K[i0-1]; k[17] = K[i0+16]
+    if (i0 + LG_IPT <= m) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(K + i0);
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            uint4 a = __ldg(q + v);
+            k[1 + 4 * v] = a.x; k[2 + 4 * v] = a.y; k[3 + 4 * v] = a.z; k[4 + 4 * v] = a.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < LG_IPT; j++) k[1 + j] = (i0 + j < m) ? __ldg(K + i0 + j) : 0u;
+    }
+    k[0] = (i0 > 0 && i0 <= m) ? __ldg(K + i0 - 1) : 0u;
+    k[LG_IPT + 1] = (i0 + LG_IPT < m) ? __ldg(K + i0 + LG_IPT) : 0u;
+    // forced-head bits of slots i0 .. i0+16 (i0 is a multiple of 16)
+    uint32_t fw = (i0 < m) ? __ldg(forced + (i0 >> 5)) : 0u;
+    uint32_t fbits = (fw >> (i0 & 31)) & 0xffffu;
+    if (i0 + LG_IPT < m) {
+        uint32_t nxt = ((i0 & 31) == 16) ? __ldg(forced + (i0 >> 5) + 1) : (fw >> 16);
+        fbits |= (nxt & 1u) << 16;
+    }
+    uint32_t head = 0;                           // bit j: slot i0+j starts a group (bit 16: the slot after the chunk)
+#pragma unroll
+    for (int j = 0; j <= LG_IPT; j++) {
+        uint32_t i = i0 + j;
+        bool h = (i == 0) | (i >= m) | (k[j + 1] != k[j]) | ((fbits >> j) & 1u);
+        head |= (h ? 1u : 0u) << j;
+    }
+    uint32_t act = 0;                            // bit j: slot i0+j is tied with a neighbour
+#pragma unroll
+    for (int j = 0; j < LG_IPT; j++) {
+        bool a = (i0 + j < m) && !(((head >> j) & 1u) && ((head >> (j + 1)) & 1u));
+        act |= (a ? 1u : 0u) << j;
+    }
+    uint32_t cnt = __popc(act), btot;
+    uint32_t inc = block_incl_scan<OpSum>(cnt, s_w, &btot);
+    if (warp_id() == 0) {
+        uint32_t prefix = tile_lookback<OpSum>(S, tile, btot, tile + 1 == ntiles, d_total);
+        if (lane_id() == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    uint32_t at = s_prefix + inc - cnt;
+    while (act) {
+        uint32_t j = __ffs(act) - 1;
+        act &= act - 1;
+        uint32_t i = i0 + j;
+        aslot[at] = i; apos[at] = __ldg(P + i); ahead[at] = ((head >> j) & 1u) ? i : 0u;
+        at++;
+    }
+}
+
 struct OutMaxInPlace {
     uint32_t *a;
     __device__ void operator()(uint64_t i, uint32_t exc, uint32_t v) const { a[i] = exc > v ? exc : v; }
