@@ -323,14 +323,38 @@ __global__ void __launch_bounds__(BLK) k_lcp_direct(const void *__restrict__ pte
                                                     const uint32_t *__restrict__ sa, uint32_t *lcp, uint32_t cap,
                                                     uint32_t *capped) {
     uint32_t r = blockIdx.x * BLK + threadIdx.x;
-    if (r >= n) return;
-    if (r == 0) { lcp[0] = 0; return; }
-    uint32_t a = sa[r - 1], b = sa[r];
-    uint32_t room = n - (a > b ? a : b);
-    uint32_t limit = room < cap ? room : cap;
-    uint32_t h = text_match<BITS>(ptext, a, b, limit);
-    lcp[r] = h;
-    if (h == cap && room > cap) atomicAdd(capped, 1u);
+    const bool live = r < n;
+    uint32_t h = 0, room = 0;
+    if (BITS == 8) {
+        if (live && r > 0) {
+            uint32_t a = sa[r - 1], b = sa[r];
+            room = n - (a > b ? a : b);
+            uint32_t limit = room < cap ? room : cap;
+            h = text_match<BITS>(ptext, a, b, limit);
+        }
+    } else {
+        // Packed text: the first window of suffix sa[r] serves the pairs (r-1, r) AND (r, r+1): every lane
+        // loads its own window once and takes its left neighbour's from the lane below (lane 0 loads
+        // both) -- the kernel is bound by the number of divergent window loads, and this halves them.
+        constexpr int PB = (BITS == 8 ? 4 : BITS);
+        constexpr uint32_t CPW = 32 / PB;
+        uint32_t b = live ? sa[r] : 0u;
+        uint32_t xb = live ? text_bits<PB>(ptext, b) : 0u;
+        uint32_t a = __shfl_up_sync(FULL, b, 1), xa = __shfl_up_sync(FULL, xb, 1);
+        if (lane_id() == 0 && live && r > 0) { a = sa[r - 1]; xa = text_bits<PB>(ptext, a); }
+        if (live && r > 0) {
+            room = n - (a > b ? a : b);
+            uint32_t limit = room < cap ? room : cap;
+            uint32_t x = xa ^ xb;
+            uint32_t first = x ? (uint32_t)(__ffs(x) - 1) / PB : CPW;       // equal leading chars inside the window
+            if (first < CPW || limit <= CPW) h = first < limit ? first : limit;
+            else h = CPW + text_match<BITS>(ptext, a + CPW, b + CPW, limit - CPW);
+        }
+    }
+    if (live) {
+        lcp[r] = h;
+        if (r > 0 && h == cap && room > cap) atomicAdd(capped, 1u);
+    }
 }
 
 // lcp-only entry points: the caller's table must be a permutation of 0..n-1 (every LCP
