@@ -431,7 +431,7 @@ def run_gpu(args):
                 g = b / 1e9 / (phase_ms[k] / 1e3)
                 phases_roof[k] = {"GBps": round(g, 1), "frac": round(g / peak, 4)}
         n_ind = len(ind)
-        roof = {"bound": "hbm", "kernel": "induce pass kernels (k_induce3<L|S> on 2-bit text; mean of the %d persistent launches per build)" % n_ind,
+        roof = {"bound": "hbm", "kernel": "induce pass kernels (k_induce6<L|S> on 2-bit text; mean of the %d persistent launches per build)" % n_ind,
                 "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
                 "traffic_source": traffic_src,

@@ -603,7 +603,8 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
         const uint32_t span = (uint32_t)(h + kc > 0xffffffffull ? 0xffffffffull : h + kc);
         bool local_ok = false;
         bool try_local = allow_local;
-        if (try_local) {                        // probe ~4096 elements: counting inside a group is quadratic in its size
+        if (try_local && na >= (1u << 20)) {    // probe ~4096 elements: counting inside a group is quadratic in its size
+                                                // (a short list is cheap either way: no probe, no extra host round trip)
             CU_TRY(c, cudaMemsetAsync(sm + 24, 0, 16, c->stream));   // [24] overflow, [25] members of big groups, [26] max size
             uint32_t stride = na / 4096u; if (stride < 1) stride = 1;
             uint32_t samples = cdiv(na, stride);

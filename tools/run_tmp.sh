@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m "gpu and not slow" -q --tb=short -x > gpurun_out/gpu_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests.log; tail -3 gpurun_out/gpu_tests.log
-timeout 200 python tools/phase_times.py 100000000 --kinds=dna,dna_nl 2>&1 | grep -o '"lcp_phases_ms[^}]*}'
+timeout 1300 python -m pytest tests -m "gpu" -q --tb=short -x --durations=4 > gpurun_out/gpu_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests.log; tail -9 gpurun_out/gpu_tests.log
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02d.json 2> gpurun_out/bench_r02d.err; echo "bench exit $?"; tail -c 1500 gpurun_out/bench_r02d.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/ref_r02d.json 2>> gpurun_out/bench_r02d.err; tail -c 600 gpurun_out/ref_r02d.json
+tools/gpu_launches.sh r02h 100000000 dna | tail -22
