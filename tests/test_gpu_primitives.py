@@ -102,9 +102,12 @@ def _classify_cases():
     return out
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["three_kernel", "fused"])
+@pytest.mark.parametrize("fused", [False, True, "tma"], ids=["three_kernel", "fused", "fused_bulk_copy"])
 @pytest.mark.parametrize("name,t", _classify_cases(), ids=lambda x: x if isinstance(x, str) else "")
-def test_classify(ctx, name, t, fused):
+def test_classify(ctx, name, t, fused, monkeypatch):
+    if fused == "tma":                        # tile loads by cp.async.bulk + mbarrier (opt-in variant)
+        monkeypatch.setenv("B200SA_CLASSIFY_TMA", "1")
+    fused = bool(fused)
     t = np.ascontiguousarray(t)
     ty = oracle.types(t)                      # 0 S, 1 L, 2 Valley (reference semantics)
     sbit, lbit, hist, pos = _classify(ctx, t, fused)

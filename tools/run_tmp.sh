@@ -1,5 +1,9 @@
 mkdir -p gpurun_out
-timeout 1300 python -m pytest tests -m "gpu" -q --tb=short -x --durations=4 > gpurun_out/gpu_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests.log; tail -9 gpurun_out/gpu_tests.log
-timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02d.json 2> gpurun_out/bench_r02d.err; echo "bench exit $?"; tail -c 1500 gpurun_out/bench_r02d.json
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/ref_r02d.json 2>> gpurun_out/bench_r02d.err; tail -c 600 gpurun_out/ref_r02d.json
-tools/gpu_launches.sh r02h 100000000 dna | tail -22
+timeout 600 python -m pytest tests/test_gpu_primitives.py tests/test_gpu_parity.py -m "gpu and not slow" -q --tb=short -x > gpurun_out/gpu_tests_tma.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests_tma.log; tail -4 gpurun_out/gpu_tests_tma.log
+for i in 1 2; do
+python tools/phase_times.py --kinds=dna 100000000 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('TMA', d['phases_ms'])"
+B200SA_CLASSIFY_NO_TMA=1 python tools/phase_times.py --kinds=dna 100000000 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('NOTMA', d['phases_ms'])"
+done
+tools/gpu_ncu_full.sh r02i induce6 "k_induce6" 2 2 | tail -3
+tools/gpu_ncu_full.sh r02i classify "k_classify_fused" 1 1 | tail -3
+python tools/steplog.py 100000000 > gpurun_out/steplog_v6.txt 2>&1; tail -5 gpurun_out/steplog_v6.txt
