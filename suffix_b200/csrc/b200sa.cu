@@ -656,9 +656,8 @@ static int lms_direct_sort(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **lis
 // 5 = warp-private tile streams + 16-bit carried chars with producer-side refresh + staged stores
 // (2-bit text), 6 = 3's block-wide tiles + 5's 16-bit carried chars (2-bit text; default there).  B200SA_INDUCE=1|2|3|4|5 forces a variant (profiles/README.md compares them).
 static int induce_variant_env() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("B200SA_INDUCE"); v = e ? atoi(e) : 0; }
-    return v;
+    const char *e = getenv("B200SA_INDUCE");       // read per call: tests switch variants inside one process
+    return e ? atoi(e) : 0;
 }
 static int induce_variant(int bits) {
     int v = induce_variant_env();
@@ -694,11 +693,16 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
     A.run_alive = A.run_scratch + TILE;
     A.cmd = sm + 336;
     A.steplog = nullptr;
+    A.blocklog_step = 0;
     A.carry = 0;
     { static int rs = -1; if (rs < 0) { const char *e = getenv("B200SA_RUN_STREAK"); rs = e ? atoi(e) : 0; } A.run_streak = (uint32_t)rs; }
     if (getenv("B200SA_STEPLOG")) {
-        if (ensure(c, c->steplog, 4096 * 8) == B200SA_OK) {
+        if (ensure(c, c->steplog, 8192 * 8) == B200SA_OK) {
             A.steplog = ptr<unsigned long long>(c->steplog);
+            if (const char *e = getenv("B200SA_BLOCKLOG")) {          // "<pass 0|1>:<big step index>"
+                int ps = 0, st = 0;
+                if (sscanf(e, "%d:%d", &ps, &st) == 2 && ps == (spass ? 1 : 0)) A.blocklog_step = (uint32_t)st + 1u;
+            }
             if (!spass) cudaMemsetAsync(c->steplog.p, 0, 8, c->stream);
         }
     }
@@ -709,6 +713,11 @@ static int launch_induce(b200sa_ctx *c, bool spass, const uint8_t *text, uint32_
     int bi = c->bits == 2 ? 0 : (c->bits == 4 ? 1 : 2);
     int blocks = c->cur_induce_blocks, cap = c->sm_count * c->induce_occ_v[variant][bi];
     if (blocks > cap) blocks = cap;
+    A.cascade = 0;
+    if (variant == 6 && !getenv("B200SA_NO_CASCADE")) {          // multi-round steps for the short lists of every bucket's cascade
+        A.cascade = (uint32_t)blocks * (uint32_t)TILE;
+        if (const char *e = getenv("B200SA_CASCADE_MAX")) { long v = atol(e); if (v >= 0 && (uint64_t)v < A.cascade) A.cascade = (uint32_t)v; }
+    }
     CU_TRY(c, cudaLaunchCooperativeKernel(induce_fn_v(spass, c->bits, variant), dim3(blocks), dim3(BLK), args, 0, c->stream));
     c->launches++;
     return B200SA_OK;
@@ -1922,7 +1931,7 @@ int64_t b200sa_debug_fetch(b200sa_ctx *c, int which, void *out, uint64_t cap) {
         case 4: src = c->lmslist.p; count = c->last_m; break;
         case 5: src = c->small.p ? (const void *)(ptr<uint32_t>(c->small) + 32) : nullptr; count = 10; break;
         case 6: src = c->tables.p; count = T_HIST; break;
-        case 7: src = c->steplog.p; count = c->steplog.p ? 8192 : 0; break;     // u64 records viewed as u32 pairs
+        case 7: src = c->steplog.p; count = c->steplog.p ? 16384 : 0; break;     // u64 records viewed as u32 pairs
         default: return B200SA_ERR_BAD_ARG;
     }
     if (!src) return 0;

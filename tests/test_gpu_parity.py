@@ -159,6 +159,34 @@ def test_long_runs(ctx, lms_path, name, t):
         assert np.array_equal(ctx.lcp(t, sa), oracle.lcp_kasai(t, want)), name
 
 
+def _two_bit_cases():
+    rng = np.random.default_rng(11)
+    runs = []
+    for k in range(300):                       # runs of the bucket chars of every length around the cascade depth
+        runs.append(np.full(int(rng.integers(1, 12)), b"ACGT"[k % 4], dtype=np.uint8))
+        runs.append(gen.dna(int(rng.integers(1, 40)), seed=k))
+    return [("dna_3M", gen.dna(3_000_000, seed=5)),
+            ("short_runs", np.concatenate(runs * 40)),
+            ("polyA_mix", np.concatenate([gen.dna(200_000, seed=2), np.full(50_000, ord("A"), np.uint8), gen.dna(100_000, seed=3),
+                                          np.full(9_000, ord("T"), np.uint8), gen.dna(1000, seed=4)])),
+            ("two_symbols", rng.integers(0, 2, 700_000).astype(np.uint8) * 2 + ord("A")),
+            ("tiny", gen.dna(37, seed=9))]
+
+
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4", "5", "6", "6_no_cascade", "6_cascade_4096"])
+@pytest.mark.parametrize("name,t", _two_bit_cases(), ids=lambda x: x if isinstance(x, str) else "")
+def test_induce_variants_two_bit(ctx, monkeypatch, variant, name, t):
+    """Every induce kernel variant for 2-bit text and the cascade steps of the default
+    one with their switch off / a low list limit: same table as the oracle."""
+    monkeypatch.setenv("B200SA_INDUCE", variant[0])
+    if variant == "6_no_cascade":
+        monkeypatch.setenv("B200SA_NO_CASCADE", "1")
+    if variant == "6_cascade_4096":
+        monkeypatch.setenv("B200SA_CASCADE_MAX", "4096")
+    t = np.ascontiguousarray(t)
+    assert np.array_equal(ctx.build(t), oracle.sais(t)), (variant, name)
+
+
 def _check_sa_properties(t, sa, samples=200000, seed=1):
     """Size-independent properties: permutation + sampled adjacent order."""
     n = len(t)
