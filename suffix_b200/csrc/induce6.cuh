@@ -52,6 +52,7 @@ __device__ __noinline__ void cascade_step(const InduceArgs &A, IndShared &sh, In
                                           uint32_t cbyte, uint32_t tiles, uint32_t *cntbuf, bool local) {
     const uint32_t G = gridDim.x, bid = blockIdx.x, tid = threadIdx.x;
     const uint32_t w = warp_id(), l = lane_id();
+    const uint32_t Gp = (G + 3u) & ~3u;                 // row stride of the count matrix [4 * CAS_R][Gp]
     const uint32_t cc = s4.code_of[cbyte];
     const uint32_t len = sh.seg.len, base = sh.seg.base;
     uint16_t *pc = reinterpret_cast<uint16_t *>(A.pred);
@@ -132,7 +133,7 @@ __device__ __noinline__ void cascade_step(const InduceArgs &A, IndShared &sh, In
         uint32_t d = tid / CAS_R, j = tid % CAS_R;
         uint32_t v = (uint32_t)(sel4(d, T0, T1, T2, T3) >> (12u * j)) & 0xfffu;
         if (local) { tot[tid] = v; bef[tid] = 0u; }
-        else if (active) cntbuf[(size_t)tid * G + bid] = v;
+        else if (active) cntbuf[(size_t)tid * Gp + bid] = v;
     }
     if (!local) {
         __syncthreads();
@@ -140,13 +141,13 @@ __device__ __noinline__ void cascade_step(const InduceArgs &A, IndShared &sh, In
         grid.sync();
         IND_MARK(2)
 #pragma unroll 1
-        for (uint32_t k = w; k < (uint32_t)(4 * CAS_R); k += NWARP) {       // one bin row per warp
+        for (uint32_t k = w; k < (uint32_t)(4 * CAS_R); k += NWARP) {       // one bin row per warp, four blocks per load
             uint32_t ts = 0, bs = 0;
-#pragma unroll 2
-            for (uint32_t b = l; b < tiles; b += 32) {
-                uint32_t v = __ldcg(cntbuf + (size_t)k * G + b);
-                ts += v;
-                bs += b < bid ? v : 0u;
+            for (uint32_t b4 = 4u * l; b4 < tiles; b4 += 128u) {
+                uint4 v = __ldcg(reinterpret_cast<const uint4 *>(cntbuf + (size_t)k * Gp + b4));
+                uint32_t x0 = v.x, x1 = b4 + 1u < tiles ? v.y : 0u, x2 = b4 + 2u < tiles ? v.z : 0u, x3 = b4 + 3u < tiles ? v.w : 0u;
+                ts += x0 + x1 + x2 + x3;
+                bs += (b4 < bid ? x0 : 0u) + (b4 + 1u < bid ? x1 : 0u) + (b4 + 2u < bid ? x2 : 0u) + (b4 + 3u < bid ? x3 : 0u);
             }
             ts = __reduce_add_sync(FULL, ts); bs = __reduce_add_sync(FULL, bs);
             if (l == 0) { tot[k] = ts; bef[k] = bs; }
