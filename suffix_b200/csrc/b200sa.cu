@@ -183,6 +183,25 @@ static int read_words(b200sa_ctx *c, const uint32_t *dsrc, int count) {
 // Single-pass scan (k_scan_lb, common.cuh): one launch, the input functor is evaluated once
 // per element.  The tile descriptors live in c->scan_state and are epoch-tagged, so nothing
 // is cleared between scans; a (re)allocated buffer is zeroed once (epochs start at 2).
+// Scan descriptors for a kernel that embeds tile_lookback (same buffer and epochs as dev_scan).
+static int scan_state_for(b200sa_ctx *c, uint32_t nb, ScanState *S) {
+    size_t need = (size_t)nb * 28 + 64;
+    if (c->scan_state.cap < need) {
+        TRY(ensure(c, c->scan_state, need * 2));
+        CU_TRY(c, cudaMemsetAsync(c->scan_state.p, 0, c->scan_state.cap, c->stream));
+        c->scan_tiles_cap = (uint32_t)((c->scan_state.cap - 64) / 28);
+    }
+    uint8_t *basep = ptr<uint8_t>(c->scan_state);
+    S->ticket = reinterpret_cast<uint32_t *>(basep);
+    S->agg = reinterpret_cast<unsigned long long *>(basep + 64);
+    S->incl = S->agg + c->scan_tiles_cap;
+    S->pk = S->incl + c->scan_tiles_cap;
+    S->flag = reinterpret_cast<uint32_t *>(S->pk + c->scan_tiles_cap);
+    c->scan_epoch += 2;
+    S->epoch = c->scan_epoch;
+    return B200SA_OK;
+}
+
 template <class Op, class InF, class OutF>
 static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, typename Op::T *d_total) {
     typedef typename Op::T T;
@@ -191,40 +210,10 @@ static int dev_scan(b200sa_ctx *c, InF in, OutF out, uint64_t n, typename Op::T 
         return B200SA_OK;
     }
     uint32_t nb = cdiv(n, SCAN_CHUNK);
-    size_t need = (size_t)nb * 20 + 64;
-    if (c->scan_state.cap < need) {
-        TRY(ensure(c, c->scan_state, need * 2));
-        CU_TRY(c, cudaMemsetAsync(c->scan_state.p, 0, c->scan_state.cap, c->stream));
-        c->scan_tiles_cap = (uint32_t)((c->scan_state.cap - 64) / 20);
-    }
     ScanState S;
-    uint8_t *basep = ptr<uint8_t>(c->scan_state);
-    S.ticket = reinterpret_cast<uint32_t *>(basep);
-    S.agg = reinterpret_cast<unsigned long long *>(basep + 64);
-    S.incl = S.agg + c->scan_tiles_cap;
-    S.flag = reinterpret_cast<uint32_t *>(S.incl + c->scan_tiles_cap);
-    c->scan_epoch += 2;
-    S.epoch = c->scan_epoch;
+    TRY(scan_state_for(c, nb, &S));
     LAUNCH(c, (k_scan_lb<Op, InF, OutF>), nb, in, out, n, nb, S, d_total);
     CU_TRY(c, cudaGetLastError());
-    return B200SA_OK;
-}
-
-// Scan descriptors for a kernel that embeds tile_lookback (same buffer and epochs as dev_scan).
-static int scan_state_for(b200sa_ctx *c, uint32_t nb, ScanState *S) {
-    size_t need = (size_t)nb * 20 + 64;
-    if (c->scan_state.cap < need) {
-        TRY(ensure(c, c->scan_state, need * 2));
-        CU_TRY(c, cudaMemsetAsync(c->scan_state.p, 0, c->scan_state.cap, c->stream));
-        c->scan_tiles_cap = (uint32_t)((c->scan_state.cap - 64) / 20);
-    }
-    uint8_t *basep = ptr<uint8_t>(c->scan_state);
-    S->ticket = reinterpret_cast<uint32_t *>(basep);
-    S->agg = reinterpret_cast<unsigned long long *>(basep + 64);
-    S->incl = S->agg + c->scan_tiles_cap;
-    S->flag = reinterpret_cast<uint32_t *>(S->incl + c->scan_tiles_cap);
-    c->scan_epoch += 2;
-    S->epoch = c->scan_epoch;
     return B200SA_OK;
 }
 

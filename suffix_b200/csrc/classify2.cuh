@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(BLK) k_classify_fused(const uint8_t *__restric
             s_lms[k++] = (uint32_t)(w * 32 + j);
         }
     }
-    if (tid == 0) tile_publish<OpSum>(S, tile, btot);       // the walk follows the histogram: by then the
+    if (tid == 0) tile_publish_u32(S, tile, btot);       // the walk follows the histogram: by then the
                                                             // predecessors have published inclusive prefixes
     // ---- histogram: warp-uniform candidate bytes first (small alphabets finish here)
     {
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(BLK) k_classify_fused(const uint8_t *__restric
         }
     }
     if (wp == 0) {
-        uint32_t prefix = tile_walk<OpSum>(S, tile, btot, tile + 1 == ntiles, d_m);
+        uint32_t prefix = tile_walk_u32(S, tile, btot, tile + 1 == ntiles, d_m);
         if (l == 0) s_prefix = prefix;
     }
     __syncthreads();

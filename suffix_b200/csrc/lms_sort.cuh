@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(BLK) k_lms_groups1(const uint32_t *__restrict_
     uint32_t cnt = __popc(act), btot;
     uint32_t inc = block_incl_scan<OpSum>(cnt, s_w, &btot);
     if (warp_id() == 0) {
-        uint32_t prefix = tile_lookback<OpSum>(S, tile, btot, tile + 1 == ntiles, d_total);
+        if (lane_id() == 0) tile_publish_u32(S, tile, btot);
+        uint32_t prefix = tile_walk_u32(S, tile, btot, tile + 1 == ntiles, d_total);
         if (lane_id() == 0) s_prefix = prefix;
     }
     __syncthreads();
