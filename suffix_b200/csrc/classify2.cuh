@@ -225,22 +225,23 @@ __global__ void __launch_bounds__(BLK) k_classify_fused(const uint8_t *__restric
             atomicAdd(&h[((c[j >> 2] >> ((j & 3) * 8)) & 0xffu) + 256u * cls], 1u);
         }
     }
+    __syncthreads();
+    // warp 0 walks the look-back chain; meanwhile the other warps flush the tile's histogram.  12 k tiles
+    // adding to the same few global words serialise in L2 (measured), so HIST_COPIES interleaved copies
+    // are summed by k_hist_fold
     if (wp == 0) {
         uint32_t prefix = tile_walk_u32(S, tile, btot, tile + 1 == ntiles, d_m);
         if (l == 0) s_prefix = prefix;
-    }
-    __syncthreads();
-    // 12 k tiles adding to the same few global words serialise in L2 (measured: 47 % of this
-    // kernel's stall samples); HIST_COPIES interleaved copies are summed by k_hist_fold
-    {
+    } else {
         uint32_t *hcopy = hist768 + (size_t)(tile % HIST_COPIES) * 768u;
-        for (int k = tid; k < 768; k += BLK) {
+        for (int k = tid - 32; k < 768; k += BLK - 32) {
             uint32_t v = 0;
 #pragma unroll
             for (int ww = 0; ww < NWARP; ww++) v += s_hist[ww][k];
             if (v) atomicAdd(&hcopy[k], v);
         }
     }
+    __syncthreads();
     if (lmspos_desc) {
         const uint32_t base = s_prefix;
         for (uint32_t k = tid; k < btot; k += BLK) lmspos_desc[base + k] = s_lms[k];
