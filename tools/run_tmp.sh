@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02f.json 2> gpurun_out/bench_r02f.err; echo "bench exit $?"; python -c "
-import json; d=json.loads(open('gpurun_out/bench_r02f.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e'], d['sa_only'], d['phase_ms'], d['roofline']['frac'], d['cpu_baseline'])"
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/ref_r02f.json 2>> gpurun_out/bench_r02f.err; tail -c 700 gpurun_out/ref_r02f.json
-tools/gpu_launches.sh r02k 100000000 dna | tail -24
-tools/gpu_ncu_full.sh r02k classify "k_classify_fused" 1 1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_primitives.py tests/test_gpu_parity.py -m "gpu and not slow" -q --tb=short -x > gpurun_out/gpu_tests_q.log 2>&1; tail -2 gpurun_out/gpu_tests_q.log
+python tools/phase_times.py --kinds=dna 100000000 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('FLUSH', d['phases_ms'])"
+python tools/phase_times.py --kinds=dna 100000000 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('FLUSH', d['phases_ms'])"
+bash tools/sanitize.sh

@@ -15,17 +15,28 @@ cases = [("dna", gen.dna(300_000)), ("dna_nl", gen.dna(200_001, newline_tail=Tru
          ("runs", np.concatenate([gen.dna(5000), np.full(20000, 78, np.uint8), gen.dna(5000), np.full(300, 65, np.uint8)])),
          ("periodic", np.tile(np.frombuffer(b"abcab", np.uint8), 20000)),
          ("tiled", gen.tiled(gen.fixture("AP009048_10000.fasta"), 120_000))]
-for variant in ("", "1", "2", "3", "4", "5"):
+rng = np.random.default_rng(3)
+runs = []
+for k in range(300):
+    runs.append(np.full(int(rng.integers(1, 12)), b"ACGT"[k % 4], dtype=np.uint8))
+    runs.append(gen.dna(int(rng.integers(1, 40)), seed=k))
+cases.append(("short_runs", np.concatenate(runs * 8)))
+for variant in ("", "1", "2", "3", "4", "5", "6:no_cascade", "6:cascade_4096", "6:classify_tma"):
+    os.environ.pop("B200SA_NO_CASCADE", None); os.environ.pop("B200SA_CASCADE_MAX", None); os.environ.pop("B200SA_CLASSIFY_TMA", None)
     if variant:
-        os.environ["B200SA_INDUCE"] = variant
+        os.environ["B200SA_INDUCE"] = variant[0]
+    if variant.endswith("no_cascade"): os.environ["B200SA_NO_CASCADE"] = "1"
+    if variant.endswith("cascade_4096"): os.environ["B200SA_CASCADE_MAX"] = "4096"
+    if variant.endswith("classify_tma"): os.environ["B200SA_CLASSIFY_TMA"] = "1"
     c2 = _lib.Context(0)
-    for name, t in (cases if not variant else cases[:2] + cases[4:5]):
+    for name, t in (cases if not variant else cases[:2] + cases[4:5] + cases[-1:]):
         sa, lcp = c2.build_lcp(t)
         want = oracle.sais(t)
         assert np.array_equal(sa, want), (variant, name)
         assert np.array_equal(lcp, oracle.lcp_kasai(t, want)), (variant, name)
     c2.close()
-os.environ.pop("B200SA_INDUCE", None)
+for k in ("B200SA_INDUCE", "B200SA_NO_CASCADE", "B200SA_CASCADE_MAX", "B200SA_CLASSIFY_TMA"):
+    os.environ.pop(k, None)
 for name, t in cases[:4]:
     want = oracle.sais(t)
     os.environ["B200SA_LCP_LINEAR"] = "1"
