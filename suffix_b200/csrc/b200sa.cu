@@ -237,22 +237,22 @@ static int radix_pass(b200sa_ctx *c, DigF dig, MoveF mv, uint64_t n) {
 
 // Sorts (ka,va) by the low `bits` of the key with the one-sweep passes of
 // common.cuh; *kout/*vout point at the buffer pair holding the result.
-template <class K>
-static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, uint64_t n, int bits,
+template <class K, int OSI>
+static int sort_pairs_t(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, uint64_t n, int bits,
                       K **kout, uint32_t **vout) {
     *kout = ka;
     *vout = va;
     if (n == 0 || bits <= 0) return B200SA_OK;
     int npass = (bits + 7) / 8;
     if (npass > OS_MAX_PASSES) npass = OS_MAX_PASSES;
-    uint32_t tiles = cdiv(n, TILE);
+    uint32_t tiles = cdiv(n, OSI * BLK);
     size_t status_bytes = (size_t)tiles * 256 * 8;
     TRY(ensure(c, c->os_hist, OS_MAX_PASSES * 256 * 4 + 64));
     TRY(ensure(c, c->os_status, status_bytes));
     uint32_t *ghist = ptr<uint32_t>(c->os_hist);
     uint32_t *ticket = ghist + OS_MAX_PASSES * 256;
     CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
-    uint32_t hb = tiles < 1184u ? tiles : 1184u;
+    uint32_t hb = cdiv(n, TILE) < 1184u ? cdiv(n, TILE) : 1184u;
     {
         size_t shm = (size_t)NWARP * npass * 256 * 4;
         auto kfn = k_os_hist<K, LoadArr<K>>;
@@ -263,7 +263,7 @@ static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, u
     LAUNCH(c, k_os_scan, (uint32_t)npass, ghist);
     for (int p = 0; p < npass; p++) {
         CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
-        LAUNCH(c, (k_os_pass<K, LoadArr<K>, LoadArr<uint32_t>>), tiles, LoadArr<K>{ka}, LoadArr<uint32_t>{va}, kb, vb, n,
+        LAUNCH(c, (k_os_pass<K, LoadArr<K>, LoadArr<uint32_t>, OSI>), tiles, LoadArr<K>{ka}, LoadArr<uint32_t>{va}, kb, vb, n,
                (uint32_t)(8 * p), ghist + p * 256,
                reinterpret_cast<volatile unsigned long long *>(c->os_status.p), ticket + p);
         K *tk = ka; ka = kb; kb = tk;
@@ -275,9 +275,19 @@ static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, u
     return B200SA_OK;
 }
 
+// Large inputs take wider tiles (16 keys per thread for 32-bit keys, 12 for 64-bit keys: what fits 48 KB of
+// static shared memory): half the tiles, look-backs and per-tile scans per key (LMS sort 1.57 -> 1.44 ms).
+template <class K>
+static int sort_pairs(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb, uint64_t n, int bits,
+                      K **kout, uint32_t **vout) {
+    if (n >= (1u << 20) && !getenv("B200SA_SORT_NARROW"))
+        return sort_pairs_t<K, (sizeof(K) == 4 ? 16 : 12)>(c, ka, va, kb, vb, n, bits, kout, vout);
+    return sort_pairs_t<K, ITEMS>(c, ka, va, kb, vb, n, bits, kout, vout);
+}
+
 // Same sort, but the first pass reads its (key, value) items from functors (no materialised
 // input arrays); at least one pass runs, so the result always lands in a buffer pair.
-template <class K, class KeyF, class ValF>
+template <class K, class KeyF, class ValF, int OSI = ITEMS>
 static int sort_pairs_from(b200sa_ctx *c, KeyF keyf, ValF valf, K *ka, uint32_t *va, K *kb, uint32_t *vb, uint64_t n,
                            int bits, K **kout, uint32_t **vout) {
     *kout = ka;
@@ -286,14 +296,14 @@ static int sort_pairs_from(b200sa_ctx *c, KeyF keyf, ValF valf, K *ka, uint32_t 
     int npass = (bits + 7) / 8;
     if (npass < 1) npass = 1;
     if (npass > OS_MAX_PASSES) npass = OS_MAX_PASSES;
-    uint32_t tiles = cdiv(n, TILE);
+    uint32_t tiles = cdiv(n, OSI * BLK);
     size_t status_bytes = (size_t)tiles * 256 * 8;
     TRY(ensure(c, c->os_hist, OS_MAX_PASSES * 256 * 4 + 64));
     TRY(ensure(c, c->os_status, status_bytes));
     uint32_t *ghist = ptr<uint32_t>(c->os_hist);
     uint32_t *ticket = ghist + OS_MAX_PASSES * 256;
     CU_TRY(c, cudaMemsetAsync(ghist, 0, OS_MAX_PASSES * 256 * 4 + 64, c->stream));
-    uint32_t hb = tiles < 1184u ? tiles : 1184u;
+    uint32_t hb = cdiv(n, TILE) < 1184u ? cdiv(n, TILE) : 1184u;
     {
         size_t shm = (size_t)NWARP * npass * 256 * 4;
         auto kfn = k_os_hist<K, KeyF>;
@@ -304,10 +314,10 @@ static int sort_pairs_from(b200sa_ctx *c, KeyF keyf, ValF valf, K *ka, uint32_t 
     LAUNCH(c, k_os_scan, (uint32_t)npass, ghist);
     volatile unsigned long long *status = reinterpret_cast<volatile unsigned long long *>(c->os_status.p);
     CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
-    LAUNCH(c, (k_os_pass<K, KeyF, ValF>), tiles, keyf, valf, ka, va, n, 0u, ghist, status, ticket);
+    LAUNCH(c, (k_os_pass<K, KeyF, ValF, OSI>), tiles, keyf, valf, ka, va, n, 0u, ghist, status, ticket);
     for (int p = 1; p < npass; p++) {
         CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
-        LAUNCH(c, (k_os_pass<K, LoadArr<K>, LoadArr<uint32_t>>), tiles, LoadArr<K>{ka}, LoadArr<uint32_t>{va}, kb, vb, n,
+        LAUNCH(c, (k_os_pass<K, LoadArr<K>, LoadArr<uint32_t>, OSI>), tiles, LoadArr<K>{ka}, LoadArr<uint32_t>{va}, kb, vb, n,
                (uint32_t)(8 * p), ghist + p * 256, status, ticket + p);
         K *tk = ka; ka = kb; kb = tk;
         uint32_t *tv = va; va = vb; vb = tv;
@@ -527,9 +537,20 @@ static int lms_direct_sort_t(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **l
     uint32_t *sm = ptr<uint32_t>(c->small);
     uint32_t *Ks, *Ps;
     TRY(mark(c, "lms_sort"));
-    TRY((sort_pairs_from<uint32_t>(c, LmsKeyDesc<BITS>{W, ptr<uint32_t>(c->lmsdesc)},
-                                   LmsValDesc{ptr<uint32_t>(c->lmsdesc)}, ptr<uint32_t>(c->k32b), ptr<uint32_t>(c->v0),
-                                   ptr<uint32_t>(c->reduced), ptr<uint32_t>(c->v1), m, bit_length(range - 1), &Ks, &Ps)));
+    {
+        const char *e = getenv("B200SA_SORT_ITEMS");            // keys per thread of the one-sweep passes: 8 | 16
+        const bool wide = e ? atoi(e) == 16 : (m >= (1u << 20) && !getenv("B200SA_SORT_NARROW"));
+        LmsKeyDesc<BITS> kf{W, ptr<uint32_t>(c->lmsdesc)};
+        LmsValDesc vf{ptr<uint32_t>(c->lmsdesc)};
+        if (wide)
+            TRY((sort_pairs_from<uint32_t, LmsKeyDesc<BITS>, LmsValDesc, 16>(c, kf, vf, ptr<uint32_t>(c->k32b), ptr<uint32_t>(c->v0),
+                                                                             ptr<uint32_t>(c->reduced), ptr<uint32_t>(c->v1), m,
+                                                                             bit_length(range - 1), &Ks, &Ps)));
+        else
+            TRY((sort_pairs_from<uint32_t, LmsKeyDesc<BITS>, LmsValDesc, ITEMS>(c, kf, vf, ptr<uint32_t>(c->k32b), ptr<uint32_t>(c->v0),
+                                                                                ptr<uint32_t>(c->reduced), ptr<uint32_t>(c->v1), m,
+                                                                                bit_length(range - 1), &Ks, &Ps)));
+    }
     // groups of equal windows; members of non-singleton groups -> active list
     TRY(mark(c, "lms_groups"));
     TRY(ensure(c, c->p0, (size_t)m * 4));

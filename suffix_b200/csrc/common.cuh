@@ -382,13 +382,14 @@ __global__ void __launch_bounds__(BLK) k_scan_lb(InF in, OutF out, uint64_t n, u
 // __syncthreads() before the call.  After the call (which ends with a
 // __syncthreads()):  position of item = digit_base[d] + s_wcnt[w][d] + rank[r]
 // and s_tcnt[d] = number of valid items with digit d in the tile.
-__device__ __forceinline__ void tile_rank(const uint32_t (&dig)[ITEMS], uint32_t validmask,
-                                          uint32_t (&rank)[ITEMS],
+template <int N>
+__device__ __forceinline__ void tile_rank(const uint32_t (&dig)[N], uint32_t validmask,
+                                          uint32_t (&rank)[N],
                                           uint32_t (*s_wcnt)[256], uint32_t *s_tcnt) {
     const uint32_t w = warp_id();
     const uint32_t lt = lanemask_lt();
 #pragma unroll
-    for (int r = 0; r < ITEMS; r++) {
+    for (int r = 0; r < N; r++) {
         bool valid = (validmask >> r) & 1u;
         uint32_t peers = peer_mask<8>(dig[r], valid);
         uint32_t below = __popc(peers & lt);
@@ -591,35 +592,36 @@ struct LoadArr {
     __device__ __forceinline__ K operator()(uint64_t i) const { return a[i]; }
     __device__ __forceinline__ K at(uint64_t i, uint32_t) const { return a[i]; }     // key of item i given its value
 };
-template <class K, class KeyF, class ValF>
-__global__ void __launch_bounds__(BLK, OS_MINB) k_os_pass(KeyF keyf, ValF valf, K *kout,
+// OSI items per thread: 8 (tile of 2048) or 16 (tile of 4096: half the tiles, look-backs and histogram scans per key)
+template <class K, class KeyF, class ValF, int OSI = ITEMS>
+__global__ void __launch_bounds__(BLK, (OSI > 8 ? 3 : OS_MINB)) k_os_pass(KeyF keyf, ValF valf, K *kout,
                                                  uint32_t *vout, uint64_t n, uint32_t shift,
                                                  const uint32_t *__restrict__ gbase, volatile unsigned long long *status,
                                                  uint32_t *ticket) {
     __shared__ uint32_t s_wcnt[NWARP][256];
     __shared__ uint32_t s_tcnt[256], s_texcl[256], s_gb[256];
     __shared__ uint32_t s_w[NWARP + 1];
-    __shared__ K s_k[TILE];
-    __shared__ uint32_t s_v[TILE];
+    __shared__ K s_k[OSI * BLK];
+    __shared__ uint32_t s_v[OSI * BLK];
     __shared__ uint32_t s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int ww = 0; ww < NWARP; ww++) s_wcnt[ww][threadIdx.x] = 0;
     __syncthreads();
     const uint32_t tile = s_tile, w = warp_id(), l = lane_id();
-    const uint64_t tb = (uint64_t)tile * TILE;
-    K key[ITEMS];
-    uint32_t val[ITEMS], d[ITEMS], rank[ITEMS], vm = 0;
+    const uint64_t tb = (uint64_t)tile * (OSI * BLK);
+    K key[OSI];
+    uint32_t val[OSI], d[OSI], rank[OSI], vm = 0;
 #pragma unroll
-    for (int r = 0; r < ITEMS; r++) {             // all values first: a key functor that gathers through the value
-        uint64_t i = tb + (uint64_t)w * (ITEMS * 32) + r * 32 + l;   // (position -> text window) then has its eight
+    for (int r = 0; r < OSI; r++) {             // all values first: a key functor that gathers through the value
+        uint64_t i = tb + (uint64_t)w * (OSI * 32) + r * 32 + l;   // (position -> text window) then has its eight
         bool valid = i < n;                                           // dependent loads in flight together
         val[r] = valid ? valf(i) : 0u;
         vm |= (valid ? 1u : 0u) << r;
     }
 #pragma unroll
-    for (int r = 0; r < ITEMS; r++) {
-        uint64_t i = tb + (uint64_t)w * (ITEMS * 32) + r * 32 + l;
+    for (int r = 0; r < OSI; r++) {
+        uint64_t i = tb + (uint64_t)w * (OSI * 32) + r * 32 + l;
         key[r] = ((vm >> r) & 1u) ? keyf.at(i, val[r]) : (K)0;
         d[r] = (uint32_t)(key[r] >> shift) & 0xffu;
     }
@@ -656,7 +658,7 @@ __global__ void __launch_bounds__(BLK, OS_MINB) k_os_pass(KeyF keyf, ValF valf, 
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < ITEMS; r++) {
+    for (int r = 0; r < OSI; r++) {
         if ((vm >> r) & 1u) {
             uint32_t p = s_texcl[d[r]] + s_wcnt[w][d[r]] + rank[r];
             s_k[p] = key[r];
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(BLK, OS_MINB) k_os_pass(KeyF keyf, ValF valf, 
     }
     __syncthreads();
     uint64_t left = n - tb;
-    uint32_t cnt_tile = left < (uint64_t)TILE ? (uint32_t)left : (uint32_t)TILE;
+    uint32_t cnt_tile = left < (uint64_t)(OSI * BLK) ? (uint32_t)left : (uint32_t)(OSI * BLK);
     for (uint32_t j = threadIdx.x; j < cnt_tile; j += BLK) {
         K k = s_k[j];
         uint32_t dst = s_gb[(uint32_t)(k >> shift) & 0xffu] + j;
