@@ -257,7 +257,7 @@ static int sort_pairs_t(b200sa_ctx *c, K *ka, uint32_t *va, K *kb, uint32_t *vb,
         size_t shm = (size_t)NWARP * npass * 256 * 4;
         auto kfn = k_os_hist<K, LoadArr<K>>;
         CU_TRY(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NWARP * OS_MAX_PASSES * 256 * 4)));
-        kfn<<<hb, BLK, shm, c->stream>>>(LoadArr<K>{ka}, n, npass, 0u, ghist);
+        kfn<<<hb, BLK, shm, c->stream>>>(LoadArr<K>{ka}, n, npass, 0u, ghist, (K *)nullptr);
         c->launches++;
     }
     LAUNCH(c, k_os_scan, (uint32_t)npass, ghist);
@@ -308,13 +308,13 @@ static int sort_pairs_from(b200sa_ctx *c, KeyF keyf, ValF valf, K *ka, uint32_t 
         size_t shm = (size_t)NWARP * npass * 256 * 4;
         auto kfn = k_os_hist<K, KeyF>;
         CU_TRY(c, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(NWARP * OS_MAX_PASSES * 256 * 4)));
-        kfn<<<hb, BLK, shm, c->stream>>>(keyf, n, npass, 0u, ghist);
+        kfn<<<hb, BLK, shm, c->stream>>>(keyf, n, npass, 0u, ghist, kb);      // kb <- the keys (free until pass 2 writes it)
         c->launches++;
     }
     LAUNCH(c, k_os_scan, (uint32_t)npass, ghist);
     volatile unsigned long long *status = reinterpret_cast<volatile unsigned long long *>(c->os_status.p);
     CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
-    LAUNCH(c, (k_os_pass<K, KeyF, ValF, OSI>), tiles, keyf, valf, ka, va, n, 0u, ghist, status, ticket);
+    LAUNCH(c, (k_os_pass<K, LoadArr<K>, ValF, OSI>), tiles, LoadArr<K>{kb}, valf, ka, va, n, 0u, ghist, status, ticket);
     for (int p = 1; p < npass; p++) {
         CU_TRY(c, cudaMemsetAsync(c->os_status.p, 0, status_bytes, c->stream));
         LAUNCH(c, (k_os_pass<K, LoadArr<K>, LoadArr<uint32_t>, OSI>), tiles, LoadArr<K>{ka}, LoadArr<uint32_t>{va}, kb, vb, n,

@@ -532,12 +532,13 @@ __device__ __forceinline__ void os_store(unsigned long long *p, unsigned long lo
 }
 constexpr int OS_MAX_PASSES = 8;
 #ifndef OS_LOOK
-#define OS_LOOK 4          // predecessor status words in flight per look-back step (measured 1..16 on 29 M pairs: 3-4 best)
+#define OS_LOOK 3          // predecessor status words in flight per look-back step (measured 1..16 on 29 M pairs: 3-4 best)
 #endif
 
 // dynamic shared memory: [NWARP][npass][256] u32 (64 KB for 8 passes)
 template <class K, class KeyF>
-__global__ void __launch_bounds__(BLK) k_os_hist(KeyF keyf, uint64_t n, int npass, uint32_t shift0, uint32_t *ghist) {
+__global__ void __launch_bounds__(BLK) k_os_hist(KeyF keyf, uint64_t n, int npass, uint32_t shift0, uint32_t *ghist,
+                                                 K *keys_out = nullptr) {
     extern __shared__ uint32_t s_dyn[];
     const uint32_t w = warp_id();
     for (int i = threadIdx.x; i < NWARP * npass * 256; i += BLK) s_dyn[i] = 0;
@@ -554,6 +555,7 @@ __global__ void __launch_bounds__(BLK) k_os_hist(KeyF keyf, uint64_t n, int npas
             uint64_t i = i0 + (uint64_t)q * BLK + threadIdx.x;
             valid[q] = i < n;
             key[q] = valid[q] ? keyf(i) : (K)0;
+            if (keys_out && valid[q]) keys_out[i] = key[q];       // gathered keys: the first pass reads them back in order
         }
 #pragma unroll
         for (int q = 0; q < 4; q++)
