@@ -1,5 +1,10 @@
 mkdir -p gpurun_out
-timeout 1300 python -m pytest tests -m "gpu" -q --tb=short -x --durations=3 > gpurun_out/gpu_tests.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests.log; tail -8 gpurun_out/gpu_tests.log
-timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02g.json 2> gpurun_out/bench_r02g.err; echo "bench exit $?"; python -c "
-import json; d=json.loads(open('gpurun_out/bench_r02g.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['sa_only'], d['phase_ms'], d['roofline']['frac'], d['cpu_baseline']['gpu_matches_oracle'], d['gpu_launches'])"
-tools/gpu_launches.sh r02l 100000000 dna | tail -24
+timeout 600 python -m pytest tests/test_gpu_parity.py -m "gpu and not slow" -q --tb=short -x -k "lcp or medium or adversarial or long_runs" > gpurun_out/gpu_tests_q.log 2>&1; tail -2 gpurun_out/gpu_tests_q.log
+for v in units nounits units nounits; do
+if [ $v = nounits ]; then export B200SA_LCP_NO_UNITS=1; else unset B200SA_LCP_NO_UNITS; fi
+python tools/phase_times.py --kinds=dna,dna_nl 100000000 2>&1 | python -c "
+import sys,json
+for ln in sys.stdin:
+    if ln.startswith('{'):
+        d=json.loads(ln); print('$v', d['input'], d['lcp_phases_ms'])"
+done
