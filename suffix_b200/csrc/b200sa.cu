@@ -1015,7 +1015,10 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
         uint32_t *bad = ptr<uint32_t>(c->small) + 12;
         CU_TRY(c, cudaMemsetAsync(seen, 0, nwv * 4, c->stream));
         CU_TRY(c, cudaMemsetAsync(bad, 0, 4, c->stream));
-        LAUNCH(c, k_sa_validate, cdiv(n, BLK), d_sa, n32, seen, bad);
+        CU_TRY(c, cudaMemsetAsync(bad + 1, 0, 4, c->stream));
+        LAUNCH(c, k_sa_validate, cdiv(cdiv(n, 4), BLK), d_sa, n32, seen, bad);
+        LAUNCH(c, k_sa_validate_count, 592u, seen, n32, bad + 1);
+        LAUNCH(c, k_sa_validate_verdict, 1u, bad + 1, n32, bad);
         TRY(read_words(c, bad, 1));
         if (c->h_pin[0] != 0) {
             c->last_error = "table is not a permutation of 0..n-1 (index out of range or repeated)";
@@ -1795,7 +1798,10 @@ int b200sa_lcp_sharded(b200sa_ctx *c, uint8_t *d_text, uint64_t n, uint32_t *d_s
         uint32_t *seen = ptr<uint32_t>(c->isa), *bad = sm + 12;
         CU_TRY(c, cudaMemsetAsync(seen, 0, nwv * 4, c->stream));
         CU_TRY(c, cudaMemsetAsync(bad, 0, 4, c->stream));
-        LAUNCH(c, k_sa_validate, cdiv(n, BLK), d_sa, n32, seen, bad);
+        CU_TRY(c, cudaMemsetAsync(bad + 1, 0, 4, c->stream));
+        LAUNCH(c, k_sa_validate, cdiv(cdiv(n, 4), BLK), d_sa, n32, seen, bad);
+        LAUNCH(c, k_sa_validate_count, 592u, seen, n32, bad + 1);
+        LAUNCH(c, k_sa_validate_verdict, 1u, bad + 1, n32, bad);
         CU_TRY(c, cudaMemsetAsync(tab + T_HIST, 0, 256 * 4, c->stream));
         uint32_t hb = cdiv(n, BLK * 64);
         if (hb > 1184) hb = 1184;

@@ -225,18 +225,36 @@ __global__ void __launch_bounds__(BLK) k_bucket_tables(const uint32_t *hist768, 
     if (c == 0) *sigma = total;
 }
 
-// Standalone byte histogram (for b200sa_lcp_dev, which has no classification).
+// Which byte values occur (for b200sa_lcp_dev, which has no classification): hist256[b] = 1 for present
+// bytes -- k_alpha_from_hist only asks "> 0".  16 bytes per load, a 256-bit set per thread in registers.
 __global__ void __launch_bounds__(BLK) k_byte_hist(const uint8_t *__restrict__ text, uint64_t n, uint32_t *hist256) {
-    __shared__ uint32_t s_h[256];
-    s_h[threadIdx.x] = 0;
+    __shared__ uint32_t s_set[8];
+    if (threadIdx.x < 8) s_set[threadIdx.x] = 0;
     __syncthreads();
-    for (uint64_t i0 = (uint64_t)blockIdx.x * BLK; i0 < n; i0 += (uint64_t)gridDim.x * BLK) {
-        uint64_t i = i0 + threadIdx.x;
-        bool valid = i < n;
-        hist_add(s_h, valid ? (uint32_t)__ldg(text + i) : 0u, valid);
+    uint32_t m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto put = [&](uint32_t b) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) m[k] |= ((b >> 5) == (uint32_t)k) ? (1u << (b & 31u)) : 0u;
+    };
+    const uint64_t nv = n / 16;
+    for (uint64_t i = (uint64_t)blockIdx.x * BLK + threadIdx.x; i < nv; i += (uint64_t)gridDim.x * BLK) {
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(text) + i);
+        uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t x = wds[q];
+            if (q > 0 && x == wds[q - 1]) continue;
+            put(x & 0xffu); put((x >> 8) & 0xffu); put((x >> 16) & 0xffu); put(x >> 24);
+        }
+    }
+    if (blockIdx.x == 0) for (uint64_t i = nv * 16 + threadIdx.x; i < n; i += BLK) put(__ldg(text + i));
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t v = __reduce_or_sync(FULL, m[k]);
+        if (lane_id() == 0 && v) atomicOr(&s_set[k], v);
     }
     __syncthreads();
-    if (s_h[threadIdx.x]) atomicAdd(&hist256[threadIdx.x], s_h[threadIdx.x]);
+    if ((s_set[threadIdx.x >> 5] >> (threadIdx.x & 31)) & 1u) hist256[threadIdx.x] = 1u;
 }
 __global__ void __launch_bounds__(BLK) k_alpha_from_hist(const uint32_t *hist256, uint32_t *code_of, uint32_t *alpha,
                                                          uint32_t *sigma) {

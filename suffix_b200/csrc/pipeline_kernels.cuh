@@ -361,15 +361,36 @@ __global__ void __launch_bounds__(BLK) k_lcp_direct(const void *__restrict__ pte
 // kernel indexes text / phi with sa[r]).  *bad counts out-of-range and repeated entries.
 __global__ void __launch_bounds__(BLK) k_sa_validate(const uint32_t *__restrict__ sa, uint32_t n, uint32_t *seen,
                                                      uint32_t *bad) {
-    uint32_t r = blockIdx.x * BLK + threadIdx.x;
-    if (r >= n) return;
-    uint32_t s = sa[r];
-    bool wrong = s >= n;
-    if (!wrong) {
-        uint32_t bit = 1u << (s & 31);
-        wrong = (atomicOr(&seen[s >> 5], bit) & bit) != 0;
+    // fire-and-forget reductions (RED, no return value) into the bitmap: a repeated entry shows up as a
+    // missing bit, which k_sa_validate_count finds (n entries < n without repeats <=> n bits set)
+    uint32_t r0 = (blockIdx.x * BLK + threadIdx.x) * 4u;
+    uint32_t wrong = 0;
+    if (r0 + 4u <= n && (reinterpret_cast<uintptr_t>(sa) & 15) == 0) {
+        uint4 v = *reinterpret_cast<const uint4 *>(sa + r0);
+        uint32_t s[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (s[q] >= n) wrong++;
+            else atomicOr(&seen[s[q] >> 5], 1u << (s[q] & 31));
+        }
+    } else {
+        for (uint32_t r = r0; r < n && r < r0 + 4u; r++) {
+            uint32_t s = sa[r];
+            if (s >= n) wrong++;
+            else atomicOr(&seen[s >> 5], 1u << (s & 31));
+        }
     }
-    if (wrong) atomicAdd(bad, 1u);
+    if (wrong) atomicAdd(bad, wrong);
+}
+// bad += 1 unless exactly n bits are set in seen[0 .. ceil(n/32))
+__global__ void __launch_bounds__(BLK) k_sa_validate_count(const uint32_t *__restrict__ seen, uint32_t n, uint32_t *cnt) {
+    uint32_t nw = (n + 31u) / 32u, c = 0;
+    for (uint32_t i = blockIdx.x * BLK + threadIdx.x; i < nw; i += gridDim.x * BLK) c += __popc(seen[i]);
+    c = __reduce_add_sync(FULL, c);
+    if (lane_id() == 0 && c) atomicAdd(cnt, c);
+}
+__global__ void k_sa_validate_verdict(const uint32_t *cnt, uint32_t n, uint32_t *bad) {
+    if (*cnt != n) atomicAdd(bad, 1u);
 }
 
 constexpr uint32_t PHI_NONE = 0xffffffffu;

@@ -1,10 +1,7 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m "gpu and not slow" -q --tb=short -x -k "lcp or medium or adversarial or long_runs" > gpurun_out/gpu_tests_q.log 2>&1; tail -2 gpurun_out/gpu_tests_q.log
-for v in units nounits units nounits; do
-if [ $v = nounits ]; then export B200SA_LCP_NO_UNITS=1; else unset B200SA_LCP_NO_UNITS; fi
-python tools/phase_times.py --kinds=dna,dna_nl 100000000 2>&1 | python -c "
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_sharded.py tests/test_gpu_next.py -m "gpu and not slow" -q --tb=short -x -k "lcp or bad_table or sharded or medium" > gpurun_out/gpu_tests_q.log 2>&1; tail -2 gpurun_out/gpu_tests_q.log
+python tools/phase_times.py --kinds=dna,bytes 100000000 2>&1 | python -c "
 import sys,json
 for ln in sys.stdin:
     if ln.startswith('{'):
-        d=json.loads(ln); print('$v', d['input'], d['lcp_phases_ms'])"
-done
+        d=json.loads(ln); print(d['input'], d['lcp_phases_ms'])"
