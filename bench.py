@@ -398,7 +398,8 @@ def run_gpu(args):
         total_bytes = n * world
         value = total_bytes * steps / 1e6 / (ms_dev / 1e3)
         e2e = total_bytes * steps / 1e6 / (ms_e2e / 1e3)
-        # ---- roofline of the dominant kernel: k_induce (persistent, 4 launches per build)
+        # ---- roofline of the dominant kernel: the persistent induce passes (2 launches per build on the direct
+        # path, 4 on the robust path)
         m = stats["m"]
         nL = n / 2.0
         # SURVEY.md Appendix D, level 0 (w = 1 byte): L pass 4n+(w+1)(m+nL)+4nL, S pass 4n+(w+1)n+4nS
