@@ -1054,9 +1054,14 @@ static int lcp_dev(b200sa_ctx *c, const uint8_t *d_text, uint64_t n, const uint3
         sm = ptr<uint32_t>(c->small);
         CU_TRY(c, cudaMemsetAsync(sm + 8, 0, 4, c->stream));
         const uint32_t cap = 256;
-        if (c->bits == 2) LAUNCH(c, (k_lcp_direct<2>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
-        else if (c->bits == 4) LAUNCH(c, (k_lcp_direct<4>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
-        else LAUNCH(c, (k_lcp_direct<8>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
+        int lk = 2;       // runs of 32 ranks per warp = window gathers in flight per lane (2-bit text: 1 / 2 / 4 ->
+                          // 0.66 / 0.57 / 0.59 ms per 10^8 ranks; 4-bit text is best with 1)
+        if (const char *e = getenv("B200SA_LCP_K")) lk = atoi(e);
+        if (c->bits == 2 && lk == 4) LAUNCH(c, (k_lcp_direct<2, 4>), cdiv(n, BLK * 4), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
+        else if (c->bits == 2 && lk == 2) LAUNCH(c, (k_lcp_direct<2, 2>), cdiv(n, BLK * 2), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
+        else if (c->bits == 2) LAUNCH(c, (k_lcp_direct<2, 1>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
+        else if (c->bits == 4) LAUNCH(c, (k_lcp_direct<4, 1>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
+        else LAUNCH(c, (k_lcp_direct<8, 1>), cdiv(n, BLK), c->ptext, n32, d_sa, d_lcp, cap, sm + 8);
         TRY(read_words(c, sm + 8, 1));
         if (c->h_pin[0] == 0) {
             TRY(mark(c, "end"));
