@@ -1,9 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m "gpu and not slow" -q --tb=short -x -k "lcp or medium or adversarial or long_runs" > gpurun_out/gpu_tests_q.log 2>&1; tail -2 gpurun_out/gpu_tests_q.log
-for k in 1 2 4 1 2 4; do
-B200SA_LCP_K=$k python tools/phase_times.py --kinds=dna,dna_nl 100000000 2>&1 | python -c "
-import sys,json
-for ln in sys.stdin:
-    if ln.startswith('{'):
-        d=json.loads(ln); print('K$k', d['input'], d['lcp_phases_ms']['lcp_direct'])"
-done
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02h.json 2> gpurun_out/bench_r02h.err; echo "bench exit $?"; python -c "
+import json; d=json.loads(open('gpurun_out/bench_r02h.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['sa_only'], d['phase_ms'], d['roofline']['frac'], d['cpu_baseline']['gpu_matches_oracle'], d['cpu_baseline']['gpu_matches_oracle_e2e'], d['gpu_launches'], d['clocks'])"
