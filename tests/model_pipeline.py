@@ -109,7 +109,7 @@ def induce(T, SA, lms_list, lms_off, Lc, Sc, bstart, sigma=256, stats=None):
 
 
 def _multiround_chain(T, SA, c, begin, end, R, spass, bstart, fill):
-    """PLANNED device step (NOTES_ROUND1.md, idea a): one partition step that plays up
+    """The cascade step of k_induce6 (induce6.cuh, R = CAS_R = 5): one partition step that plays up
     to R chain rounds of bucket c at once.  Entry e_j of the list [begin,end) with
     l_j = min(run of c to its left, R) emits e_j - r into round r (1 <= r <= l_j) of the
     chain region, round-major then list order; if l_j < R its terminal e_j - l_j
