@@ -595,8 +595,11 @@ struct LoadArr {
     __device__ __forceinline__ K at(uint64_t i, uint32_t) const { return a[i]; }     // key of item i given its value
 };
 // OSI items per thread: 8 (tile of 2048) or 16 (tile of 4096: half the tiles, look-backs and histogram scans per key)
+#ifndef OS_MINB_WIDE
+#define OS_MINB_WIDE 3
+#endif
 template <class K, class KeyF, class ValF, int OSI = ITEMS>
-__global__ void __launch_bounds__(BLK, (OSI > 8 ? 3 : OS_MINB)) k_os_pass(KeyF keyf, ValF valf, K *kout,
+__global__ void __launch_bounds__(BLK, (OSI > 8 ? OS_MINB_WIDE : OS_MINB)) k_os_pass(KeyF keyf, ValF valf, K *kout,
                                                  uint32_t *vout, uint64_t n, uint32_t shift,
                                                  const uint32_t *__restrict__ gbase, volatile unsigned long long *status,
                                                  uint32_t *ticket) {

@@ -1,3 +1,5 @@
-mkdir -p gpurun_out
-timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_r02h.json 2> gpurun_out/bench_r02h.err; echo "bench exit $?"; python -c "
-import json; d=json.loads(open('gpurun_out/bench_r02h.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['sa_only'], d['phase_ms'], d['roofline']['frac'], d['cpu_baseline']['gpu_matches_oracle'], d['cpu_baseline']['gpu_matches_oracle_e2e'], d['gpu_launches'], d['clocks'])"
+for rep in 1 2; do
+for t in base walk minb4 minb2; do
+if [ $t = base ]; then unset B200SA_LIB; else export B200SA_LIB=$PWD/build_exp/lib_$t.so; fi
+python tools/phase_times.py --kinds=dna 100000000 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); p=d['phases_ms']; print('$t', p['classify'], p['lms_sort'], p['lms_groups'])"
+done; done
