@@ -1,5 +1,3 @@
-for rep in 1 2; do
-for t in base walk minb4 minb2; do
-if [ $t = base ]; then unset B200SA_LIB; else export B200SA_LIB=$PWD/build_exp/lib_$t.so; fi
-python tools/phase_times.py --kinds=dna 100000000 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); p=d['phases_ms']; print('$t', p['classify'], p['lms_sort'], p['lms_groups'])"
-done; done
+mkdir -p gpurun_out
+timeout 280 python -m pytest tests -m "gpu and not slow" -q --tb=short -x > gpurun_out/gpu_tests_final.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests_final.log; tail -4 gpurun_out/gpu_tests_final.log
+python -c "import __graft_entry__ as g; g.smoke()"
