@@ -660,11 +660,14 @@ static int lms_direct_sort(b200sa_ctx *c, uint32_t n, uint32_t m, uint32_t **lis
 }
 
 // ------------------------------------------------------- induce launcher
-// Kernel variants of the induce passes: 1 = one-round steps with MATCH ranking (any packing),
-// 2 = multi-round bucket steps (packed text), 3 = packed-counter ranking (2-bit text only),
-// 4 = 3 + carried predecessor chars + staged coalesced stores (2-bit text only).  Default for 2-bit
-// 5 = warp-private tile streams + 16-bit carried chars with producer-side refresh + staged stores
-// (2-bit text), 6 = 3's block-wide tiles + 5's 16-bit carried chars (2-bit text; default there).  B200SA_INDUCE=1|2|3|4|5 forces a variant (profiles/README.md compares them).
+// Kernel variants of the induce passes (profiles/README.md compares them; B200SA_INDUCE=1..6 forces one):
+//   1  one-round steps with MATCH ranking (any packing; the default for 4-bit and byte text)
+//   2  multi-round bucket steps (packed text)
+//   3  packed-counter ranking on physically aligned tiles (2-bit text)
+//   4  3 + three carried predecessor chars per byte + staged coalesced stores (2-bit text)
+//   5  warp-private tile streams + 16-bit carried chars with producer-side refresh (2-bit text)
+//   6  3's block-wide tiles + 5's carried chars + cascade steps for short chain lists (2-bit text; default there;
+//      B200SA_NO_CASCADE / B200SA_CASCADE_MAX=<entries> switch the cascade steps off / limit them)
 static int induce_variant_env() {
     const char *e = getenv("B200SA_INDUCE");       // read per call: tests switch variants inside one process
     return e ? atoi(e) : 0;
