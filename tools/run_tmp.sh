@@ -1,3 +1,2 @@
-mkdir -p gpurun_out
-timeout 280 python -m pytest tests -m "gpu and not slow" -q --tb=short -x > gpurun_out/gpu_tests_final.log 2>&1; echo "tests exit $?" >> gpurun_out/gpu_tests_final.log; tail -4 gpurun_out/gpu_tests_final.log
 python -c "import __graft_entry__ as g; g.smoke()"
+timeout 60 python bench.py --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['gpu_launches'])"
